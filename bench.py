@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""
+bench.py -- the PhaMers hot path (k-mer count -> normalise -> score) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--contigs C] [--k 4]
+
+A "step" is one pass of the whole hot path over one batch of synthetic contigs: BASELINE.json configs[1]
+("synthetic metagenome 1M contigs, 1-100 kb lognormal lengths, k=4 tetranucleotide, 1xB200"), scored against the shipped
+phage / bacteria reference features (2255 + 2255 rows, equalised) with the reference's default 'combo' method.
+Scaling is weak: every rank holds its own 1M-contig shard of the same seeded generator (rank r = contigs
+[r*C, (r+1)*C)); the only collective is the all-gather of the per-contig scores.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel), cpu_baseline (oracle port
+timed on this box's host cores, rank 0, N = 1 only), kernels (per-stage device times), contigs_per_sec.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260101
+METRIC = "bases/sec k-mer counted and scored (count + normalise + combo score per step)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contigs", type=int, default=1000000, help="contigs per GPU")
+    ap.add_argument("--k", type=int, default=4)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning experiments)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-contigs", type=int, default=800)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, sm_max, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().split("\n"):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                sm_max.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arms (oracle port; the reference is pure Python and cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_count_worker(seqs):
+    from oracle import phamers_oracle as po
+    return [po.count_string(s, 4) for s in seqs]
+
+
+def host_sample(n_contigs, seed=SEED):
+    """Same length law as the device generator; bases i.i.d. with a per-contig GC fraction."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lengths = np.clip(np.round(np.exp(rng.normal(np.log(10000.0), 1.0, size=n_contigs))), 1000, 100000).astype(np.int64)
+    seqs = []
+    for length in lengths:
+        gc = rng.uniform(0.25, 0.75)
+        p = [(1 - gc) / 2, (1 - gc) / 2, gc / 2, gc / 2]
+        seqs.append(rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(length), p=p).tobytes().decode("ascii"))
+    return seqs, int(lengths.sum())
+
+
+def cpu_pass(seqs, pos, neg, pool=None, centroids=None):
+    """One pass of the oracle port over `seqs`: interpreted counting loop (scripts/kmer.py:42-50), normalise, combo
+    score with scikit-learn as the reference calls it.  Returns seconds."""
+    import numpy as np
+    from oracle import phamers_oracle as po
+    t0 = time.perf_counter()
+    if pool is None:
+        counts = np.stack([po.count_string(s, 4) for s in seqs])
+    else:
+        n = pool._processes
+        chunks = [seqs[i::n] for i in range(n)]
+        parts = pool.map(_cpu_count_worker, chunks)
+        counts = np.zeros((len(seqs), 256), dtype=np.int64)
+        for i, part in enumerate(parts):
+            counts[i::n] = np.stack(part) if part else counts[i::n]
+    pts = po.normalize_counts(counts)
+    # centroids are passed in: the reference re-runs k-means once per scoring CALL (~2 s, phamer.py:245-246); over the
+    # full 1M-contig call that is negligible, so charging it to a small sample would understate the reference
+    po.score_points(pts, pos, neg, centroids=centroids)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port, kind 'port') with all host cores, on a bounded sample
+    of the same workload per step."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import phamers_oracle as po
+    ref = np.load(os.path.join(ROOT, "phamers_b200", "data", "reference_features.npz"))
+    n_ref = min(len(ref["positive_counts"]), len(ref["negative_counts"]))
+    pos = po.normalize_counts(ref["positive_counts"][:n_ref].astype(np.int64))
+    neg = po.normalize_counts(ref["negative_counts"][:n_ref].astype(np.int64))
+    cores = os.cpu_count() or 1
+    n_sample = max(cores * 40, 64)
+    seqs, bases = host_sample(n_sample)
+    cents = po.reference_centroids(pos, neg)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_pass(seqs[:cores], pos, neg, pool, cents)
+        times = [cpu_pass(seqs, pos, neg, pool, cents) for _ in range(args.steps)]
+    total = sum(times)
+    value = bases * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": "synthetic metagenome 1M contigs, 1-100 kb lognormal, k=4 (configs[1]); bounded sample",
+                   "sample_contigs": n_sample, "sample_bases": bases},
+        "contigs_per_sec": n_sample * args.steps / total,
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
+                         "sample": "%d contigs / %d bases per step; oracle/phamers_oracle.py (restates scripts/kmer.py:42-50, "
+                                   "phamer.py:303-313) over a %d-process pool, scikit-learn k-means + kNN per step"
+                                   % (n_sample, bases, cores)},
+        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from phamers_b200 import _lib, ops, parallel, pipeline, references
+
+    for opt in args.opt:
+        name, value = opt.split("=")
+        _lib.set_option(name, int(value))
+    caps = _lib.device_caps()
+    peaks = measured_peaks()
+
+    # ---- workload (untimed) ----
+    n = args.contigs
+    seq, offsets = ops.synth_contigs(SEED, rank * n, n)
+    bases = int(offsets[-1].item())
+    pos, neg = references.load_reference_features(equalize=True)
+    centroids = references.reference_centroids(pos, neg)               # reference-only preprocessing, cached, untimed
+    scorer = pipeline.ContigScorer(pos, neg, centroids=centroids, kmer_length=args.k)
+    n_refs = pos.shape[0] + neg.shape[0]
+    n_cent = centroids[0].shape[0] + centroids[1].shape[0]
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    count_ms, score_ms = [], []
+
+    def step(timed):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(stream)
+        counts, freq = ops.count_cuda(seq, offsets, args.k, counts=True, freq=True)
+        e1.record(stream)
+        knn, km, combo = ops.score_cuda(freq, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)
+        e2.record(stream)
+        if world > 1:
+            gathered = parallel.gather_scores(combo, [n] * world)
+        else:
+            gathered = combo
+        if timed:
+            step.events.append((e0, e1, e2))
+        return counts, gathered
+    step.events = []
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.kernel_launches
+    t_start, t_end = ev(), ev()
+    torch.cuda.synchronize()
+    t_start.record(stream)
+    for _ in range(args.steps):
+        counts, gathered = step(True)
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.kernel_launches - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    for e0, e1, e2 in step.events:
+        count_ms.append(e0.elapsed_time(e1))
+        score_ms.append(e1.elapsed_time(e2))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    tot_bases = torch.tensor([bases], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_bases, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    all_bases = float(tot_bases.item())
+
+    # ---- sanity inside the bench: row sums of the last step's counts (clean synthetic bases) ----
+    lengths = offsets[1:] - offsets[:-1]
+    assert bool((counts.sum(dim=1, dtype=torch.int64) == lengths - (args.k - 1)).all()), "count row sums are wrong"
+    assert bool(torch.isfinite(gathered).all()) and gathered.numel() == n * world
+
+    # ---- end to end through the public API with HOST buffers (copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host_seq = torch.empty((bases,), dtype=torch.uint8, pin_memory=True)
+            host_seq.copy_(seq)
+            host_off = torch.empty((n + 1,), dtype=torch.int64, pin_memory=True)
+            host_off.copy_(offsets)
+            torch.cuda.synchronize()
+            scorer.score_host(host_seq, host_off)                     # warm-up (staging allocation)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                host_scores = scorer.score_host(host_seq, host_off)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            assert np.array_equal(host_scores, gathered[rank * n:(rank + 1) * n].cpu().numpy())
+            e2e = {"value": all_bases * args.e2e_steps / dt, "unit": "bases/s",
+                   "h2d_bytes_per_step": int(bases + 8 * (n + 1)), "d2h_bytes_per_step": int(8 * n),
+                   "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "api": "phamers_b200.pipeline.ContigScorer.score_host (pinned host bases + offsets in, host scores out)"}
+            del host_seq
+        except RuntimeError as exc:                                   # e.g. pinned allocation refused
+            e2e = {"value": None, "unit": "bases/s", "error": str(exc)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    c_ms = statistics.mean(count_ms)
+    s_ms = statistics.mean(score_ms)
+    bins = 4 ** args.k
+    count_bytes = bases * 1.0 + n * bins * 4.0 + n * bins * 8.0        # ASCII read once + u32 counts + f64 features written once
+    score_flops = 2.0 * n * (n_refs + n_cent) * bins
+    count_roof = {"bound": "hbm", "achieved": count_bytes / (c_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "traffic": None, "kernel": "kmer_hist_kernel", "peak_source": peaks["source"]}
+    count_roof["frac"] = count_roof["achieved"] / count_roof["peak"]
+    score_roof = {"bound": "tensor", "achieved": score_flops / (s_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                  "unit": "TFLOP/s", "traffic": None, "kernel": "score_exact_kernel (float64 CUDA cores, not tensor cores yet)",
+                  "peak_source": peaks["source"]}
+    score_roof["frac"] = score_roof["achieved"] / score_roof["peak"]
+    dominant = count_roof if c_ms >= s_ms else score_roof
+
+    # ---- CPU baseline (oracle port, rank 0, N = 1 only, bounded sample) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import phamers_oracle as po
+        seqs, sample_bases = host_sample(args.cpu_sample_contigs)
+        dt = cpu_pass(seqs, pos, neg, None, (centroids[0], centroids[1]))
+        cpu = {"value": sample_bases / dt, "unit": "bases/s", "cores": 1, "kind": "port",
+               "host_cores": os.cpu_count(),
+               "sample": "%d contigs / %d bases of the same length law, one pass in %.1f s: interpreted counting loop on 1 core "
+                         "(as the reference runs), scikit-learn kNN + centroid loop (k-means untimed)" % (len(seqs), sample_bases, dt)}
+
+    value = all_bases * args.steps / (elapsed_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 bases -> u32 counts -> f64 features/scores", "data": "synthetic",
+        "config": {"workload": "synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=%d (BASELINE configs[1]), "
+                               "scored against %d shipped reference rows + %d centroids, method combo"
+                               % (n, args.k, n_refs, n_cent),
+                   "contigs_per_gpu": n, "bases_per_gpu": bases, "seed": SEED,
+                   "l2_policy": "inputs (%.1f GB of bases per step) are far larger than the 126 MB L2" % (bases / 1e9),
+                   "parallelism": "contigs sharded over %d GPU(s), references replicated, one NCCL all-gather of scores" % world,
+                   "options": args.opt},
+        "contigs_per_sec": n * world * args.steps / (elapsed_ms * 1e-3),
+        "kernels": {"count_ms": c_ms, "score_ms": s_ms, "count_roofline": count_roof, "score_roofline": score_roof},
+        "roofline": dominant, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "device": {"sm": "%d.%d" % (caps.sm_major, caps.sm_minor), "sm_count": caps.sm_count},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+/*
+ * phamers_b200 -- C-ABI of the B200-native PhaMers hot path (k-mer count -> normalise -> score).
+ *
+ * The reference (jondeaton/PhaMers) is pure Python and has no FFI of its own; the boundary it exposes
+ * for this path is the module-level API of scripts/kmer.py and scripts/phamer.py.  The entry points
+ * below are what a ctypes binding inside those two modules calls; each one cites
+ * the reference lines it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every `d_*` pointer is a DEVICE pointer on the
+ *     current CUDA device, every `h_*` pointer is a HOST pointer (pinned memory recommended).
+ *   - All launches go to `stream` (a cudaStream_t / CUstream passed as void*; NULL = default stream).
+ *     Device entry points never allocate and never synchronise; scratch memory is caller-owned
+ *     (`d_workspace`, sized by the matching *_workspace_bytes function).  Host-buffer entry points
+ *     (phm_*_host) own a lazily created staging pool and return after the result is in host memory.
+ *   - Return value: 0 = ok, negative = error (PHM_E_*); phm_last_error() gives the message of the
+ *     most recent failure on the calling thread.
+ *   - Bin order everywhere is the reference's: symbols 'ATGC' (A=0 T=1 G=2 C=3), first base most
+ *     significant (scripts/kmer.py:28,44-50,183-196).  Only those four upper-case bytes are symbols;
+ *     any other byte voids every window it touches.
+ */
+#ifndef PHAMERS_B200_H
+#define PHAMERS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHM_VERSION 100            /* 0.1.0 */
+
+#define PHM_OK             0
+#define PHM_E_ARG         -1       /* bad argument (k out of range, null pointer, misaligned buffer) */
+#define PHM_E_CUDA        -2       /* a CUDA runtime call failed; see phm_last_error() */
+#define PHM_E_WORKSPACE   -3       /* workspace too small */
+#define PHM_E_UNSUPPORTED -4       /* not an sm_100 device / option not built */
+
+/* flags for phm_kmer_count* */
+#define PHM_COUNT_CANONICAL  1u    /* fold reverse complements: out bins = 136 / 512 / 2080 for k = 4 / 5 / 6 */
+#define PHM_COUNT_NAIVE      2u    /* use the simple (slow) cross-check kernel */
+
+typedef struct phm_caps {
+    int32_t device;                /* CUDA device ordinal */
+    int32_t sm_major, sm_minor;    /* 10, 0 on B200 */
+    int32_t sm_count;              /* 148 on B200 */
+    int32_t max_smem_optin;        /* bytes of shared memory per CTA (227 KB on B200) */
+    int64_t hbm_bytes;             /* total device memory */
+} phm_caps;
+
+int          phm_version(void);
+const char  *phm_last_error(void);
+int          phm_device_caps(phm_caps *out);
+
+/* Number of output bins for k (4^k), or for the canonical fold (136 / 512 / 2080 ...). */
+int64_t      phm_num_bins(int k, uint32_t flags);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  sequence pack.  Replaces kmer.sequence_to_integers (scripts/kmer.py:183-196): ASCII bases ->
+ *     2-bit codes in reference order (A=0 T=1 G=2 C=3), 16 bases per uint32 (base i of a word in bits
+ *     2i+1:2i), plus one validity bit per base, 32 bases per uint32 (bit i = base i is one of ATGC).
+ *     d_seq must be 16-byte aligned.  d_codes holds ceil(n_bases/16) words, d_valid ceil(n_bases/32).
+ * ------------------------------------------------------------------------------------------- */
+int phm_pack_fasta(const uint8_t *d_seq, int64_t n_bases, uint32_t *d_codes, uint32_t *d_valid, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2+K3  k-mer histogram with fused (optional canonical) fold and normalisation.
+ *     Replaces the loop of kmer.count_string (scripts/kmer.py:42-50) over every record of
+ *     kmer.count_file (scripts/kmer.py:137-139) and kmer.normalize_counts (scripts/kmer.py:209-221).
+ *
+ *     d_seq      ASCII bases of all contigs laid end to end (record text with line breaks already
+ *                removed, i.e. what str(record.seq) is in the reference); 16-byte aligned.
+ *     d_offsets  int64[n_contigs + 1]; contig i = d_seq[d_offsets[i] .. d_offsets[i+1]).
+ *     k          1..6.
+ *     d_counts   uint32[n_contigs * bins]          (may be NULL)  -- bit-exact with the reference.
+ *     d_freq     float64[n_contigs * bins]         (may be NULL)  -- counts / row sum, IEEE division
+ *                exactly as numpy does it; an all-zero row gives NaN like kmer.py:219-220.
+ *     d_workspace / workspace_bytes  scratch from phm_kmer_count_workspace_bytes().
+ * ------------------------------------------------------------------------------------------- */
+size_t phm_kmer_count_workspace_bytes(int64_t n_contigs, int64_t n_bases, int k, uint32_t flags);
+int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_contigs, int k, uint32_t flags,
+                   uint32_t *d_counts, double *d_freq,
+                   void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Same histogram from the packed form produced by phm_pack_fasta (multi-k passes over one pack). */
+int phm_kmer_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, const int64_t *d_offsets,
+                          int64_t n_contigs, int k, uint32_t flags, uint32_t *d_counts, double *d_freq,
+                          void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* kmer.normalize_counts on its own (scripts/kmer.py:209-221) for counts that are already on the device. */
+int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, int64_t bins, double *d_freq, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4+K5  scoring.  Replaces phamer_scorer.knn_score_points / kmeans_score_points / combo_score_points
+ *     (scripts/phamer.py:240-256,268-273,303-313), i.e. learning.knn (scripts/learning.py:118-128),
+ *     learning.closest_to (:59-66) and phamer_scorer.proximity_metric (scripts/phamer.py:198-210).
+ *     Clustering of the reference sets (learning.kmeans, :131-146) is reference-only preprocessing and
+ *     stays on the host: the caller passes the centroids.
+ *
+ *     d_points        float64[n_points * dim]   query features (rows of kmer.normalize_counts)
+ *     d_refs          float64[n_refs * dim]     positive rows first, then negative (phamer.py:186)
+ *     n_positive      number of leading rows of d_refs labelled 1 (phamer.py:187)
+ *     d_cent_pos/neg  float64[n_cent_* * dim]   centroids of the positive / negative clusters
+ *     k_neighbors     odd, 1..15 (reference default 3, phamer.py:79)
+ *     d_knn           float64[n_points]  +1 / -1 vote                    (may be NULL)
+ *     d_kmeans        float64[n_points]  tanh((e_neg-e_pos)/(e_pos+e_neg))  (may be NULL)
+ *     d_combo         float64[n_points]  knn + kmeans                     (may be NULL)
+ *     A query row holding NaN (zero-count contig) gets NaN in all three outputs.
+ * ------------------------------------------------------------------------------------------- */
+size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg, int dim);
+int phm_score(const double *d_points, int64_t n_points, int dim,
+              const double *d_refs, int64_t n_refs, int64_t n_positive,
+              const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+              int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
+              void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic workload (bench / tests only): contigs with lengths clip(round(exp(N(ln 10000, 1))), 1000,
+ * 100000), bases i.i.d. over ATGC with a per-contig GC fraction in
+ * U(0.25, 0.75), counter-based RNG keyed by (seed, global contig index) so that a shard generated on
+ * any rank equals the same rows of the single-GPU workload.
+ *   phm_synth_lengths: d_lengths int64[n]   for contigs first_contig .. first_contig + n - 1
+ *   phm_synth_bases:   fills d_seq[d_offsets[i] .. d_offsets[i+1])
+ * ------------------------------------------------------------------------------------------- */
+int phm_synth_lengths(uint64_t seed, int64_t first_contig, int64_t n_contigs, int64_t *d_lengths, void *stream);
+int phm_synth_bases(uint64_t seed, int64_t first_contig, int64_t n_contigs, const int64_t *d_offsets,
+                    uint8_t *d_seq, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHAMERS_B200_H */

@@ -1,0 +1,612 @@
+// K1 / K2 / K3: sequence pack, k-mer histogram with fused fold + normalise, and the simple cross-check kernel.
+//
+// Replaces the interpreted per-base loop of kmer.count_string (reference scripts/kmer.py:42-50) and
+// kmer.normalize_counts (scripts/kmer.py:209-221).  See DESIGN.md for the layout and the roofline.
+//
+// Histogram kernel in one paragraph: persistent warps pull groups of contigs from a global counter.  A warp owns
+// a private table of 32-bit counters in shared memory and walks its contig in 512-byte steps (one 128-bit
+// streaming load per lane).  Each lane turns its 16 ASCII bases into 32 bits of 2-bit reference codes with a
+// handful of SWAR instructions (kmer_swar.h), fetches the 16 bases that follow from its neighbour lane with a
+// shuffle, and bumps one counter per window with `red.shared.add`.  For k = 4 the windows are 5-mers taken at
+// every SECOND base (a 5-mer holds two consecutive 4-mers), which halves the number of shared-memory atomics;
+// the 1024-bin 5-mer table is projected back onto the 256 4-mer bins when the contig is finished.  Chunks that
+// hold a non-ATGC byte or a contig boundary take a warp-uniform slow path with an exact per-base blank mask.
+#include "phm_common.cuh"
+#include "kmer_swar.h"
+
+namespace phm {
+
+struct Dec {
+    uint32_t s;       // 16 two-bit codes, first base in the top bits
+    uint32_t blank;   // both bits of a base set = that base is not a symbol or lies outside the contig
+};
+
+__device__ __forceinline__ Dec decode_chunk(uint4 raw, int lo, int hi) {
+    uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    Dec d;
+    d.s = codes16_be(w);
+    d.blank = 0;
+    if (any_invalid16(w)) d.blank = blank_mask16_be(w);
+    if (lo > 0 || hi < 16) d.blank |= outside_mask16_be(lo, hi);
+    return d;
+}
+
+template <int K, int STRIDE>
+struct HistCfg {
+    static constexpr int W = K + STRIDE - 1;             // window width in bases
+    static constexpr int TAB_BINS = 1 << (2 * W);
+    static constexpr int TAB_BYTES = TAB_BINS * 4;
+    static constexpr int OUT_BINS = 1 << (2 * K);
+    static constexpr int DIRECT_BYTES = (STRIDE > 1) ? OUT_BINS * 4 : 0;
+    static constexpr int ALIGN = TAB_BYTES < 16 ? 16 : TAB_BYTES;
+    static constexpr int WARP_BYTES = ALIGN + DIRECT_BYTES;
+};
+
+// --------------------------------------------------------------------------------------------------
+// the histogram kernel
+// --------------------------------------------------------------------------------------------------
+template <int K, int STRIDE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
+                 uint32_t *__restrict__ counts, double *__restrict__ freq,
+                 const uint16_t *__restrict__ rc_lut, const uint16_t *__restrict__ compact_lut, int out_bins,
+                 unsigned long long *work_counter, int contigs_per_item) {
+    using Cfg = HistCfg<K, STRIDE>;
+    constexpr int W = Cfg::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // tables are aligned to their own size so that (base | offset) is the address of a bin
+    const uint32_t base = (smem_u32(smem_raw) + (uint32_t)Cfg::ALIGN - 1u) & ~((uint32_t)Cfg::ALIGN - 1u);
+    const uint32_t tab = base + (uint32_t)warp * Cfg::ALIGN;
+    const uint32_t direct = base + (uint32_t)WARPS * Cfg::ALIGN + (uint32_t)warp * Cfg::DIRECT_BYTES;
+    const uint32_t vst = (STRIDE > 1) ? direct : tab;     // where the folded 4^K histogram is staged
+    const bool canonical = rc_lut != nullptr;
+
+    if (Cfg::TAB_BINS >= 128) {
+        for (int i = lane; i < Cfg::TAB_BINS / 4; i += 32) sts_v4_zero(tab + 16u * i);
+    } else {
+        for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
+    }
+    if (STRIDE > 1)
+        for (int i = lane; i < Cfg::OUT_BINS / 4; i += 32) sts_v4_zero(direct + 16u * i);
+    __syncwarp();
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1ull);
+        item = __shfl_sync(FULL, item, 0);
+        const int64_t first = (int64_t)item * contigs_per_item;
+        if (first >= n_contigs) break;
+        const int64_t last = (first + contigs_per_item < n_contigs) ? first + contigs_per_item : n_contigs;
+
+        for (int64_t c = first; c < last; ++c) {
+            const int64_t start = off[c];
+            const int64_t end = off[c + 1];
+            if (end - start >= K) {
+                const int64_t c0 = start >> 4;
+                const int nchunks = (int)(((end + 15) >> 4) - c0);
+                const int startrel = (int)(start - (c0 << 4));
+                const int endrel = (int)(end - (c0 << 4));
+                const uint4 *gp = reinterpret_cast<const uint4 *>(seq) + c0;
+                const int n_iter = (nchunks + 31) >> 5;
+
+                auto load = [&](int it) -> uint4 {
+                    const int ci = it * 32 + lane;
+                    return (ci < nchunks) ? ldg_stream(gp + ci) : make_uint4(0u, 0u, 0u, 0u);
+                };
+                auto decode = [&](uint4 raw, int it) -> Dec {
+                    const int ci = it * 32 + lane;
+                    if (ci >= nchunks) return Dec{0u, 0xFFFFFFFFu};
+                    const int pos = ci << 4;
+                    return decode_chunk(raw, startrel - pos, endrel - pos);
+                };
+
+                uint4 raw = load(0);
+                Dec cur = decode(raw, 0);
+                raw = load(1);
+                for (int it = 0; it < n_iter; ++it) {
+                    const Dec nxt = decode(raw, it + 1);
+                    raw = load(it + 2);
+                    uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
+                    const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
+                    if (lane == 31) hi_s = wrap_s;
+                    const bool dirty = (cur.blank != 0u) | ((lane == 0) & (nxt.blank != 0u));
+                    if (!__any_sync(FULL, dirty)) {
+#pragma unroll
+                        for (int p = 0; p < 16; p += STRIDE)
+                            red_shared_inc(tab | window_offset<W>(cur.s, hi_s, p));
+                    } else {
+                        uint32_t hi_b = __shfl_down_sync(FULL, cur.blank, 1);
+                        const uint32_t wrap_b = __shfl_sync(FULL, nxt.blank, 0);
+                        if (lane == 31) hi_b = wrap_b;
+#pragma unroll
+                        for (int p = 0; p < 16; p += STRIDE) {
+                            const uint32_t bl = window_bits<W>(cur.blank, hi_b, p);
+                            const uint32_t idx = window_bits<W>(cur.s, hi_s, p);
+                            if (bl == 0u) {
+                                red_shared_inc(tab + 4u * idx);
+                            } else if (STRIDE > 1) {
+                                // a partly blank window still holds up to STRIDE clean k-mers
+#pragma unroll
+                                for (int s = 0; s < STRIDE; ++s) {
+                                    const int sh = 2 * (W - K - s);
+                                    const uint32_t kmask = (1u << (2 * K)) - 1u;
+                                    if (((bl >> sh) & kmask) == 0u) red_shared_inc(direct + 4u * ((idx >> sh) & kmask));
+                                }
+                            }
+                        }
+                    }
+                    cur = nxt;
+                }
+            }
+            __syncwarp();
+
+            // ---- fold the window table onto the 4^K bins, staged in `vst`; row total ----
+            unsigned long long total = 0;
+            if (STRIDE > 1) {
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    uint32_t v = lds_u32(direct + 4u * y);
+                    const uint4 q = lds_v4(tab + 16u * y);                 // windows whose first k-mer is y
+                    v += q.x + q.y + q.z + q.w;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) v += lds_u32(tab + 4u * (cc * Cfg::OUT_BINS + y));   // ... whose second k-mer is y
+                    sts_u32(direct + 4u * y, v);
+                    total += v;
+                }
+            } else {
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) total += lds_u32(tab + 4u * y);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+            const double dtotal = (double)total;
+            __syncwarp();
+
+            if (!canonical) {
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t v = lds_u32(vst + 4u * y);
+                    if (counts) counts[c * Cfg::OUT_BINS + y] = v;
+                    if (freq) freq[c * Cfg::OUT_BINS + y] = (double)v / dtotal;
+                }
+            } else {
+                // reverse-complement fold in place: every bin above its partner adds itself onto the partner
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t r = rc_lut[y];
+                    if (r < (uint32_t)y) {
+                        const uint32_t v = lds_u32(vst + 4u * y);
+                        if (v) red_shared_add(vst + 4u * r, v);
+                    }
+                }
+                __syncwarp();
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t r = rc_lut[y];
+                    if ((uint32_t)y <= r) {
+                        const uint32_t v = lds_u32(vst + 4u * y);
+                        const int64_t o = c * (int64_t)out_bins + compact_lut[y];
+                        if (counts) counts[o] = v;
+                        if (freq) freq[o] = (double)v / dtotal;
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- clear for the next contig ----
+            if (Cfg::TAB_BINS >= 128) {
+                for (int i = lane; i < Cfg::TAB_BINS / 4; i += 32) sts_v4_zero(tab + 16u * i);
+            } else {
+                for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
+            }
+            if (STRIDE > 1)
+                for (int i = lane; i < Cfg::OUT_BINS / 4; i += 32) sts_v4_zero(direct + 16u * i);
+            __syncwarp();
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// canonical look-up tables: rc[y] and compact[y] = rank of min(y, rc(y)) among the self-representing bins
+// --------------------------------------------------------------------------------------------------
+__global__ void canonical_lut_kernel(int k, uint16_t *rc_lut, uint16_t *compact_lut) {
+    __shared__ uint16_t rank[4096];
+    const int bins = 1 << (2 * k);
+    for (int y = threadIdx.x; y < bins; y += blockDim.x) rc_lut[y] = (uint16_t)revcomp_bin((uint32_t)y, k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint16_t r = 0;
+        for (int y = 0; y < bins; ++y) {
+            rank[y] = r;
+            if ((uint32_t)y <= rc_lut[y]) ++r;
+        }
+    }
+    __syncthreads();
+    for (int y = threadIdx.x; y < bins; y += blockDim.x) {
+        const uint32_t r = rc_lut[y];
+        compact_lut[y] = rank[r < (uint32_t)y ? r : y];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// simple cross-check kernel: one warp per contig, every lane re-reads the k bytes of its window, global atomics
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ref_symbol(uint8_t c) {
+    return c == 'A' ? 0 : c == 'T' ? 1 : c == 'G' ? 2 : c == 'C' ? 3 : -1;
+}
+
+__global__ void kmer_naive_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
+                                  int k, uint32_t *__restrict__ counts, const uint16_t *__restrict__ rc_lut,
+                                  const uint16_t *__restrict__ compact_lut, int out_bins) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < n_contigs; c += n_warps) {
+        const int64_t start = off[c], end = off[c + 1];
+        for (int64_t p = start + lane; p + k <= end; p += 32) {
+            uint32_t idx = 0;
+            bool ok = true;
+            for (int j = 0; j < k; ++j) {
+                const int s = ref_symbol(seq[p + j]);
+                ok &= s >= 0;
+                idx = idx * 4u + (uint32_t)(s & 3);
+            }
+            if (!ok) continue;
+            if (rc_lut) {
+                const uint32_t r = rc_lut[idx];
+                idx = compact_lut[r < idx ? r : idx];
+            }
+            atomicAdd(&counts[c * (int64_t)out_bins + idx], 1u);
+        }
+    }
+}
+
+// kmer.normalize_counts (scripts/kmer.py:209-221): one warp per row
+__global__ void normalize_kernel(const uint32_t *__restrict__ counts, int64_t n_rows, int64_t bins, double *__restrict__ freq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        unsigned long long total = 0;
+        for (int64_t b = lane; b < bins; b += 32) total += counts[r * bins + b];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+        const double dt = (double)total;
+        for (int64_t b = lane; b < bins; b += 32) freq[r * bins + b] = (double)counts[r * bins + b] / dt;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// K1 pack: 32 bases per thread -> two code words + one validity word
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t squeeze_pairs(uint32_t x) {      // one bit per 2-bit pair, order kept
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
+__global__ void pack_kernel(const uint8_t *__restrict__ seq, int64_t n_bases, uint32_t *__restrict__ codes,
+                            uint32_t *__restrict__ valid) {
+    const int64_t n_groups = (n_bases + 31) >> 5;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t vbits = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t chunk = 2 * g + h;
+            const int64_t b0 = chunk << 4;
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            int hi = 0;
+            if (b0 + 16 <= n_bases) {
+                const uint4 raw = ldg_stream(reinterpret_cast<const uint4 *>(seq) + chunk);
+                w[0] = raw.x; w[1] = raw.y; w[2] = raw.z; w[3] = raw.w;
+                hi = 16;
+            } else if (b0 < n_bases) {
+                hi = (int)(n_bases - b0);
+                for (int i = 0; i < hi; ++i) w[i >> 2] |= (uint32_t)seq[b0 + i] << (8 * (i & 3));
+            }
+            if (b0 < n_bases) {
+                uint32_t blank = blank_mask16_be(w) | outside_mask16_be(0, hi);
+                codes[chunk] = codes16_be(w) & ~blank;
+                vbits |= (~squeeze_pairs(blank) & 0xFFFFu) << (16 * (1 - h));
+            }
+        }
+        valid[g] = vbits;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// histogram from the packed form: same warp-per-contig walk, 16 bases per lane per step
+// --------------------------------------------------------------------------------------------------
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+kmer_hist_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ valid,
+                        const int64_t *__restrict__ off, int64_t n_contigs, uint32_t *__restrict__ counts,
+                        double *__restrict__ freq, const uint16_t *__restrict__ rc_lut,
+                        const uint16_t *__restrict__ compact_lut, int out_bins,
+                        unsigned long long *work_counter, int contigs_per_item) {
+    using Cfg = HistCfg<K, 1>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = (smem_u32(smem_raw) + (uint32_t)Cfg::ALIGN - 1u) & ~((uint32_t)Cfg::ALIGN - 1u);
+    const uint32_t tab = base + (uint32_t)warp * Cfg::ALIGN;
+    const bool canonical = rc_lut != nullptr;
+    for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
+    __syncwarp();
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1ull);
+        item = __shfl_sync(FULL, item, 0);
+        const int64_t first = (int64_t)item * contigs_per_item;
+        if (first >= n_contigs) break;
+        const int64_t last = (first + contigs_per_item < n_contigs) ? first + contigs_per_item : n_contigs;
+        for (int64_t c = first; c < last; ++c) {
+            const int64_t start = off[c], end = off[c + 1];
+            if (end - start >= K) {
+                const int64_t c0 = start >> 4;
+                const int nchunks = (int)(((end + 15) >> 4) - c0);
+                const int startrel = (int)(start - (c0 << 4));
+                const int endrel = (int)(end - (c0 << 4));
+                auto fetch = [&](int it) -> Dec {
+                    const int ci = it * 32 + lane;
+                    if (ci >= nchunks) return Dec{0u, 0xFFFFFFFFu};
+                    const int64_t chunk = c0 + ci;
+                    Dec d;
+                    d.s = codes[chunk];
+                    const uint32_t v16 = (valid[chunk >> 1] >> (16 * (1 - (int)(chunk & 1)))) & 0xFFFFu;
+                    d.blank = 0u;
+                    if (v16 != 0xFFFFu) {                       // spread 16 validity bits to blank pairs
+                        uint32_t x = (~v16) & 0xFFFFu;
+                        x = (x | (x << 8)) & 0x00FF00FFu;
+                        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+                        x = (x | (x << 2)) & 0x33333333u;
+                        x = (x | (x << 1)) & 0x55555555u;
+                        d.blank = x | (x << 1);
+                    }
+                    const int pos = ci << 4;
+                    if (startrel - pos > 0 || endrel - pos < 16) d.blank |= outside_mask16_be(startrel - pos, endrel - pos);
+                    return d;
+                };
+                const int n_iter = (nchunks + 31) >> 5;
+                Dec cur = fetch(0);
+                for (int it = 0; it < n_iter; ++it) {
+                    const Dec nxt = fetch(it + 1);
+                    uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
+                    const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
+                    if (lane == 31) hi_s = wrap_s;
+                    const bool dirty = (cur.blank != 0u) | ((lane == 0) & (nxt.blank != 0u));
+                    if (!__any_sync(FULL, dirty)) {
+#pragma unroll
+                        for (int p = 0; p < 16; ++p) red_shared_inc(tab | window_offset<K>(cur.s, hi_s, p));
+                    } else {
+                        uint32_t hi_b = __shfl_down_sync(FULL, cur.blank, 1);
+                        const uint32_t wrap_b = __shfl_sync(FULL, nxt.blank, 0);
+                        if (lane == 31) hi_b = wrap_b;
+#pragma unroll
+                        for (int p = 0; p < 16; ++p)
+                            if (window_bits<K>(cur.blank, hi_b, p) == 0u) red_shared_inc(tab + window_offset<K>(cur.s, hi_s, p));
+                    }
+                    cur = nxt;
+                }
+            }
+            __syncwarp();
+            unsigned long long total = 0;
+            for (int y = lane; y < Cfg::OUT_BINS; y += 32) total += lds_u32(tab + 4u * y);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+            const double dtotal = (double)total;
+            if (!canonical) {
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t v = lds_u32(tab + 4u * y);
+                    if (counts) counts[c * Cfg::OUT_BINS + y] = v;
+                    if (freq) freq[c * Cfg::OUT_BINS + y] = (double)v / dtotal;
+                }
+            } else {
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t r = rc_lut[y];
+                    if (r < (uint32_t)y) {
+                        const uint32_t v = lds_u32(tab + 4u * y);
+                        if (v) red_shared_add(tab + 4u * r, v);
+                    }
+                }
+                __syncwarp();
+                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                    const uint32_t r = rc_lut[y];
+                    if ((uint32_t)y <= r) {
+                        const uint32_t v = lds_u32(tab + 4u * y);
+                        const int64_t o = c * (int64_t)out_bins + compact_lut[y];
+                        if (counts) counts[o] = v;
+                        if (freq) freq[o] = (double)v / dtotal;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
+            __syncwarp();
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host-side launchers
+// --------------------------------------------------------------------------------------------------
+struct CountWorkspace {
+    unsigned long long *counter;     // 8 bytes (work counter), 256-byte slot
+    uint16_t *rc_lut;                // 4096 entries
+    uint16_t *compact_lut;           // 4096 entries
+};
+static constexpr size_t kCountWorkspaceBytes = 256 + 2 * 4096 * sizeof(uint16_t);
+
+static CountWorkspace carve(void *ws) {
+    CountWorkspace w;
+    unsigned char *p = static_cast<unsigned char *>(ws);
+    w.counter = reinterpret_cast<unsigned long long *>(p);
+    w.rc_lut = reinterpret_cast<uint16_t *>(p + 256);
+    w.compact_lut = w.rc_lut + 4096;
+    return w;
+}
+
+int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
+int hist_contigs_per_item = 4;
+
+template <int K, int STRIDE, int WARPS>
+static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, double *freq,
+                       const uint16_t *rc, const uint16_t *compact, int out_bins, unsigned long long *counter,
+                       cudaStream_t st) {
+    using Cfg = HistCfg<K, STRIDE>;
+    const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN;
+    auto kern = kmer_hist_kernel<K, STRIDE, WARPS>;
+    PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) { set_error("histogram kernel does not fit on an SM (smem %zu)", smem); return PHM_E_UNSUPPORTED; }
+    int64_t grid = (int64_t)per_sm * sm_count();
+    const int64_t items = (n + hist_contigs_per_item - 1) / hist_contigs_per_item;
+    const int64_t need = (items + WARPS - 1) / WARPS;
+    if (grid > need) grid = need < 1 ? 1 : need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(seq, off, n, counts, freq, rc, compact, out_bins, counter,
+                                                    hist_contigs_per_item);
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}
+
+template <int K, int WARPS>
+static int launch_hist_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *off, int64_t n,
+                              uint32_t *counts, double *freq, const uint16_t *rc, const uint16_t *compact,
+                              int out_bins, unsigned long long *counter, cudaStream_t st) {
+    using Cfg = HistCfg<K, 1>;
+    const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN;
+    auto kern = kmer_hist_packed_kernel<K, WARPS>;
+    PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) { set_error("packed histogram kernel does not fit on an SM (smem %zu)", smem); return PHM_E_UNSUPPORTED; }
+    int64_t grid = (int64_t)per_sm * sm_count();
+    const int64_t items = (n + hist_contigs_per_item - 1) / hist_contigs_per_item;
+    const int64_t need = (items + WARPS - 1) / WARPS;
+    if (grid > need) grid = need < 1 ? 1 : need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(codes, valid, off, n, counts, freq, rc, compact, out_bins,
+                                                    counter, hist_contigs_per_item);
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}
+
+static int64_t canonical_bins(int k) {
+    int64_t n = 0;
+    for (uint32_t y = 0; y < (1u << (2 * k)); ++y) n += (y <= revcomp_bin(y, k));
+    return n;
+}
+
+}  // namespace phm
+
+using namespace phm;
+
+extern "C" int64_t phm_num_bins(int k, uint32_t flags) {
+    if (k < 1 || k > 6) return -1;
+    return (flags & PHM_COUNT_CANONICAL) ? canonical_bins(k) : ((int64_t)1 << (2 * k));
+}
+
+extern "C" size_t phm_kmer_count_workspace_bytes(int64_t, int64_t, int, uint32_t) { return kCountWorkspaceBytes; }
+
+static int prepare_count(int64_t n_contigs, int k, uint32_t flags, void *ws, size_t ws_bytes, const void *offsets,
+                         CountWorkspace *w, const uint16_t **rc, const uint16_t **compact, int *out_bins,
+                         cudaStream_t st) {
+    PHM_REQUIRE(k >= 1 && k <= 6, "k must be 1..6");
+    PHM_REQUIRE(n_contigs >= 0, "n_contigs must be >= 0");
+    PHM_REQUIRE(offsets != nullptr || n_contigs == 0, "d_offsets is null");
+    PHM_REQUIRE(ws != nullptr, "d_workspace is null");
+    if (ws_bytes < kCountWorkspaceBytes) { set_error("workspace too small: %zu < %zu", ws_bytes, kCountWorkspaceBytes); return PHM_E_WORKSPACE; }
+    *w = carve(ws);
+    PHM_CUDA_CHECK(cudaMemsetAsync(w->counter, 0, 256, st));
+    *rc = nullptr; *compact = nullptr;
+    *out_bins = 1 << (2 * k);
+    if (flags & PHM_COUNT_CANONICAL) {
+        canonical_lut_kernel<<<1, 1024, 0, st>>>(k, w->rc_lut, w->compact_lut);
+        PHM_CUDA_CHECK(cudaGetLastError());
+        *rc = w->rc_lut; *compact = w->compact_lut;
+        *out_bins = (int)canonical_bins(k);
+    }
+    return PHM_OK;
+}
+
+extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_contigs, int k, uint32_t flags,
+                              uint32_t *d_counts, double *d_freq, void *d_workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CountWorkspace w; const uint16_t *rc, *compact; int out_bins;
+    int rcode = prepare_count(n_contigs, k, flags, d_workspace, workspace_bytes, d_offsets, &w, &rc, &compact, &out_bins, st);
+    if (rcode != PHM_OK) return rcode;
+    if (n_contigs == 0) return PHM_OK;
+    PHM_REQUIRE(d_seq != nullptr, "d_seq is null");
+    PHM_REQUIRE((reinterpret_cast<uintptr_t>(d_seq) & 15u) == 0, "d_seq must be 16-byte aligned");
+    PHM_REQUIRE(d_counts != nullptr || d_freq != nullptr, "both outputs are null");
+
+    if (flags & PHM_COUNT_NAIVE) {
+        PHM_REQUIRE(d_counts != nullptr, "the naive kernel needs d_counts");
+        PHM_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, (size_t)n_contigs * out_bins * sizeof(uint32_t), st));
+        int64_t blocks = (n_contigs + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        kmer_naive_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_seq, d_offsets, n_contigs, k, d_counts, rc, compact, out_bins);
+        PHM_CUDA_CHECK(cudaGetLastError());
+        if (d_freq) return phm_normalize_counts(d_counts, n_contigs, out_bins, d_freq, stream);
+        return PHM_OK;
+    }
+    switch (k) {
+        case 1: return launch_hist<1, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 2: return launch_hist<2, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 3: return launch_hist<3, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 4:
+            if (hist_stride_for_k4 == 2)
+                return launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+            return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 5: return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 6: return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+    }
+    return PHM_E_ARG;
+}
+
+extern "C" int phm_kmer_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, const int64_t *d_offsets,
+                                     int64_t n_contigs, int k, uint32_t flags, uint32_t *d_counts, double *d_freq,
+                                     void *d_workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CountWorkspace w; const uint16_t *rc, *compact; int out_bins;
+    int rcode = prepare_count(n_contigs, k, flags, d_workspace, workspace_bytes, d_offsets, &w, &rc, &compact, &out_bins, st);
+    if (rcode != PHM_OK) return rcode;
+    if (n_contigs == 0) return PHM_OK;
+    PHM_REQUIRE(d_codes != nullptr && d_valid != nullptr, "packed inputs are null");
+    PHM_REQUIRE(d_counts != nullptr || d_freq != nullptr, "both outputs are null");
+    switch (k) {
+        case 1: return launch_hist_packed<1, 8>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 2: return launch_hist_packed<2, 8>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 3: return launch_hist_packed<3, 8>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 4: return launch_hist_packed<4, 8>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 5: return launch_hist_packed<5, 8>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 6: return launch_hist_packed<6, 4>(d_codes, d_valid, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+    }
+    return PHM_E_ARG;
+}
+
+extern "C" int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, int64_t bins, double *d_freq, void *stream) {
+    PHM_REQUIRE(n_rows >= 0 && bins > 0, "bad shape");
+    if (n_rows == 0) return PHM_OK;
+    PHM_REQUIRE(d_counts != nullptr && d_freq != nullptr, "null pointer");
+    int64_t blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    normalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_counts, n_rows, bins, d_freq);
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}
+
+extern "C" int phm_pack_fasta(const uint8_t *d_seq, int64_t n_bases, uint32_t *d_codes, uint32_t *d_valid, void *stream) {
+    PHM_REQUIRE(n_bases >= 0, "n_bases must be >= 0");
+    if (n_bases == 0) return PHM_OK;
+    PHM_REQUIRE(d_seq != nullptr && d_codes != nullptr && d_valid != nullptr, "null pointer");
+    PHM_REQUIRE((reinterpret_cast<uintptr_t>(d_seq) & 15u) == 0, "d_seq must be 16-byte aligned");
+    const int64_t groups = (n_bases + 31) >> 5;
+    int64_t blocks = (groups + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    pack_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_seq, n_bases, d_codes, d_valid);
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}

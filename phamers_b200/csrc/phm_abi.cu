@@ -1,0 +1,73 @@
+// Library-wide pieces of the C-ABI: error state, device capabilities, tuning options.
+#include <stdarg.h>
+
+#include "phm_common.cuh"
+
+namespace phm {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static int g_sm_count = 0, g_smem_optin = 0;
+
+static void query_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+}
+
+int sm_count() {
+    if (g_sm_count == 0) query_device();
+    return g_sm_count;
+}
+int max_smem_optin() {
+    if (g_smem_optin == 0) query_device();
+    return g_smem_optin;
+}
+
+extern int hist_stride_for_k4;
+extern int hist_contigs_per_item;
+
+}  // namespace phm
+
+using namespace phm;
+
+extern "C" int phm_version(void) { return PHM_VERSION; }
+
+extern "C" const char *phm_last_error(void) { return g_error; }
+
+extern "C" int phm_device_caps(phm_caps *out) {
+    PHM_REQUIRE(out != nullptr, "out is null");
+    int dev = 0;
+    PHM_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PHM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    out->device = dev;
+    out->sm_major = prop.major;
+    out->sm_minor = prop.minor;
+    out->sm_count = prop.multiProcessorCount;
+    out->max_smem_optin = (int32_t)prop.sharedMemPerBlockOptin;
+    out->hbm_bytes = (int64_t)prop.totalGlobalMem;
+    if (prop.major != 10) {
+        set_error("phamers_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+        return PHM_E_UNSUPPORTED;
+    }
+    return PHM_OK;
+}
+
+// Tuning knobs for experiments (bench.py --opt name=value).  Unknown names are an error.
+extern "C" int phm_set_option(const char *name, int64_t value) {
+    PHM_REQUIRE(name != nullptr, "name is null");
+    if (!strcmp(name, "hist_stride_k4")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k4 = (int)value; return PHM_OK; }
+    if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 1 && value <= 4096, "1..4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
+    set_error("unknown option '%s'", name);
+    return PHM_E_ARG;
+}

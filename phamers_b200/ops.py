@@ -1,0 +1,143 @@
+"""
+Tensor-native host layer over the C-ABI: device tensors in, device tensors out, everything on the current CUDA
+stream.  PyTorch is used for device memory and streams only; all arithmetic happens inside libphamers_b200.so.
+The drop-in modules (kmer.py, phamer.py) convert to the reference's NumPy dtypes on top of these.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+_workspaces = {}
+kernel_launches = 0          # kernels of libphamers_b200.so launched through this module (bench.py reports it)
+
+
+def _launched(n):
+    global kernel_launches
+    kernel_launches += n
+
+
+def _workspace(kind, nbytes):
+    dev = torch.cuda.current_device()
+    key = (kind, dev)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device="cuda")
+        _workspaces[key] = buf
+    return buf
+
+
+def _as_u8_cuda(seq):
+    if not (isinstance(seq, torch.Tensor) and seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()):
+        raise TypeError("sequence buffer must be a contiguous CUDA uint8 tensor")
+    if seq.data_ptr() % 16:
+        raise ValueError("sequence buffer must be 16-byte aligned")
+    return seq
+
+
+def num_bins(k, canonical=False):
+    n = _lib.load().phm_num_bins(int(k), _lib.PHM_COUNT_CANONICAL if canonical else 0)
+    if n < 0:
+        raise ValueError("k must be 1..6")
+    return int(n)
+
+
+def count_cuda(seq, offsets, k, canonical=False, counts=True, freq=False, naive=False):
+    """K2+K3.  seq: uint8[total bases] (contigs end to end), offsets: int64[n+1].  Returns (counts int32[n, bins] or
+    None, freq float64[n, bins] or None).  Counts are exact unsigned 32-bit values (< 2^31 for any contig this
+    library accepts), stored in an int32 tensor because torch has no first-class uint32."""
+    lib = _lib.require_cuda()
+    seq = _as_u8_cuda(seq)
+    if not (offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()):
+        raise TypeError("offsets must be a contiguous CUDA int64 tensor")
+    n = offsets.numel() - 1
+    flags = (_lib.PHM_COUNT_CANONICAL if canonical else 0) | (_lib.PHM_COUNT_NAIVE if naive else 0)
+    bins = num_bins(k, canonical)
+    out_counts = torch.empty((n, bins), dtype=torch.int32, device="cuda") if (counts or naive) else None
+    out_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda") if freq else None
+    ws_bytes = lib.phm_kmer_count_workspace_bytes(n, seq.numel(), int(k), flags)
+    ws = _workspace("count", ws_bytes)
+    check(lib.phm_kmer_count(ptr(seq), ptr(offsets), n, int(k), flags, ptr(out_counts), ptr(out_freq),
+                             ptr(ws), ws.numel(), stream_ptr()))
+    _launched((1 if n else 0) + (1 if canonical else 0) + (1 if (naive and freq and n) else 0))
+    return (out_counts if counts else None), out_freq
+
+
+def pack_cuda(seq):
+    """K1.  uint8[n] ASCII -> (codes int32[ceil(n/16)], valid int32[ceil(n/32)])."""
+    lib = _lib.require_cuda()
+    seq = _as_u8_cuda(seq)
+    n = seq.numel()
+    codes = torch.empty(((n + 15) // 16,), dtype=torch.int32, device="cuda")
+    valid = torch.empty(((n + 31) // 32,), dtype=torch.int32, device="cuda")
+    check(lib.phm_pack_fasta(ptr(seq), n, ptr(codes), ptr(valid), stream_ptr()))
+    _launched(1 if n else 0)
+    return codes, valid
+
+
+def count_packed_cuda(codes, valid, offsets, k, canonical=False, counts=True, freq=False):
+    lib = _lib.require_cuda()
+    n = offsets.numel() - 1
+    flags = _lib.PHM_COUNT_CANONICAL if canonical else 0
+    bins = num_bins(k, canonical)
+    out_counts = torch.empty((n, bins), dtype=torch.int32, device="cuda") if counts else None
+    out_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda") if freq else None
+    ws = _workspace("count", lib.phm_kmer_count_workspace_bytes(n, 0, int(k), flags))
+    check(lib.phm_kmer_count_packed(ptr(codes), ptr(valid), ptr(offsets), n, int(k), flags, ptr(out_counts),
+                                    ptr(out_freq), ptr(ws), ws.numel(), stream_ptr()))
+    _launched((1 if n else 0) + (1 if canonical else 0))
+    return out_counts, out_freq
+
+
+def normalize_cuda(counts):
+    """kmer.normalize_counts on the device: int32/uint32[n, bins] -> float64[n, bins]."""
+    lib = _lib.require_cuda()
+    if counts.dtype != torch.int32 or not counts.is_cuda:
+        raise TypeError("counts must be a CUDA int32 tensor")
+    counts = counts.contiguous()
+    two_d = counts.reshape(-1, counts.shape[-1])
+    out = torch.empty(two_d.shape, dtype=torch.float64, device="cuda")
+    check(lib.phm_normalize_counts(ptr(two_d), two_d.shape[0], two_d.shape[1], ptr(out), stream_ptr()))
+    _launched(1 if two_d.shape[0] else 0)
+    return out.reshape(counts.shape)
+
+
+def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3):
+    """K4+K5.  float64 CUDA tensors: points[n, d], refs[R, d] (positives first), centroids[C, d].
+    Returns (knn, kmeans, combo) float64[n]."""
+    lib = _lib.require_cuda()
+    tensors = [points, refs, cent_pos, cent_neg]
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float64):
+            raise TypeError("score_cuda takes CUDA float64 tensors")
+    points, refs, cent_pos, cent_neg = (t.contiguous() for t in tensors)
+    n, dim = points.shape
+    if refs.shape[1] != dim or (cent_pos.numel() and cent_pos.shape[1] != dim) or (cent_neg.numel() and cent_neg.shape[1] != dim):
+        raise ValueError("feature widths differ")
+    knn = torch.empty((n,), dtype=torch.float64, device="cuda")
+    kmeans = torch.empty((n,), dtype=torch.float64, device="cuda")
+    combo = torch.empty((n,), dtype=torch.float64, device="cuda")
+    ws_bytes = lib.phm_score_workspace_bytes(n, refs.shape[0], cent_pos.shape[0], cent_neg.shape[0], dim)
+    ws = _workspace("score", ws_bytes)
+    check(lib.phm_score(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
+                        ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
+                        ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
+    if n:
+        _launched(1 + sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]))
+    return knn, kmeans, combo
+
+
+def synth_contigs(seed, first_contig, n_contigs):
+    """Synthetic metagenome shard generated on the device.
+    Returns (seq uint8[total], offsets int64[n+1])."""
+    lib = _lib.require_cuda()
+    lengths = torch.empty((n_contigs,), dtype=torch.int64, device="cuda")
+    check(lib.phm_synth_lengths(ctypes.c_uint64(seed), int(first_contig), int(n_contigs), ptr(lengths), stream_ptr()))
+    offsets = torch.zeros((n_contigs + 1,), dtype=torch.int64, device="cuda")
+    torch.cumsum(lengths, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    seq = torch.empty(((total + 15) // 16 * 16,), dtype=torch.uint8, device="cuda")
+    check(lib.phm_synth_bases(ctypes.c_uint64(seed), int(first_contig), int(n_contigs), ptr(offsets), ptr(seq), stream_ptr()))
+    return seq[:total], offsets

@@ -1,0 +1,199 @@
+"""GPU parity tests for stage 1+2 (k-mer counting, normalising) through the C-ABI: bit-exact against the golden
+vectors from the unmodified reference, against the oracle on seeded random inputs, and through size-independent
+properties at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import phamers_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _seqs(g):
+    blob, off = g["seq_bytes"].tobytes().decode("ascii"), g["seq_offsets"]
+    return [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def _device(seq_bytes, offsets):
+    total = int(offsets[-1])
+    buf = torch.zeros(((total + 15) // 16 * 16 + 16,), dtype=torch.uint8)
+    buf[:total] = torch.from_numpy(np.array(seq_bytes[:total], dtype=np.uint8))
+    return buf.cuda(), torch.from_numpy(np.asarray(offsets, dtype=np.int64)).cuda()
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32).astype(np.int64)
+
+
+@pytest.fixture(scope="module")
+def counting(golden_dir):
+    return np.load(os.path.join(golden_dir, "counting_golden.npz"))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_counts_match_reference_golden(counting, k):
+    from phamers_b200 import kmer, ops, _lib
+    seqs = _seqs(counting)
+    want = counting["counts_k%d" % k]
+    got = kmer.count(seqs, k)
+    assert got.dtype == np.int64 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    # every kernel variant: simple cross-check kernel, stride-1 histogram for k = 4, packed input
+    d_seq, d_off = _device(counting["seq_bytes"], counting["seq_offsets"])
+    naive, _ = ops.count_cuda(d_seq, d_off, k, naive=True)
+    assert np.array_equal(_u32(naive), want)
+    if k == 4:
+        _lib.set_option("hist_stride_k4", 1)
+        try:
+            s1, _ = ops.count_cuda(d_seq, d_off, k)
+        finally:
+            _lib.set_option("hist_stride_k4", 2)
+        assert np.array_equal(_u32(s1), want)
+    codes, valid = ops.pack_cuda(d_seq)
+    packed, _ = ops.count_packed_cuda(codes, valid, d_off, k)
+    assert np.array_equal(_u32(packed), want)
+
+
+def test_dispatch_conventions_and_normalize(counting):
+    from phamers_b200 import kmer
+    seqs = _seqs(counting)
+    one = kmer.count([seqs[12]], 4)
+    assert one.shape == (256,) and np.array_equal(one, counting["dispatch_list1"])
+    three = kmer.count(seqs[8:11], 4)
+    assert three.shape == (3, 256) and np.array_equal(three, counting["dispatch_list3"])
+    norm = kmer.count(seqs[13], 4, normalize=True)
+    assert norm.dtype == np.float64 and np.array_equal(norm, counting["dispatch_str_norm"])
+    assert kmer.count(12345, 4) is None
+    assert kmer.count_string("AAAT", 4)[1] == 1                       # scripts/kmer.py:90-91
+    got = kmer.normalize_counts(counting["counts_k4"])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, counting["normalized_k4"], equal_nan=True)   # bit-identical IEEE division, NaN rows kept
+    assert np.array_equal(kmer.count(seqs[:3], 4, normalize=True), np.zeros((3, 256)))   # kmer.py:77 guard
+    rna = kmer.count_string("AUGCAUGGN", 2, symbols=kmer.RNA)
+    assert np.array_equal(rna, po.count_string("AUGCAUGGN", 2, symbols="AUGC"))
+    with pytest.raises(NotImplementedError):
+        kmer.count_string("ARND", 2, symbols=kmer.protein)
+
+
+def test_count_file_matches_reference_golden(golden_dir, tmp_path):
+    from phamers_b200 import kmer
+    g = np.load(os.path.join(golden_dir, "fasta_golden.npz"))
+    path = tmp_path / "contigs.fasta"
+    with open(path, "w", newline="") as fh:
+        fh.write(str(g["fasta_text"]))
+    for k in (4, 5, 6):
+        ids, counts = kmer.count_file(str(path), k)
+        assert [str(x) for x in ids] == [str(x) for x in g["ids"]]
+        assert counts.dtype == np.int64 and np.array_equal(counts, g["counts_k%d" % k])
+    _, freq = kmer.count_file(str(path), 4, normalize=True)
+    want = g["freq_k4"]
+    assert np.array_equal(freq, want, equal_nan=True)
+    assert kmer.count_file(str(tmp_path / "missing.fasta"), 4) == (None, None)
+
+
+def _random_workload(rng, n, dirty):
+    lengths = np.clip(np.round(np.exp(rng.normal(np.log(3000), 1.2, size=n))), 0, 60000).astype(np.int64)
+    lengths[rng.integers(0, n, size=max(1, n // 50))] = rng.integers(0, 8, size=max(1, n // 50))   # shorter than k
+    offsets = np.concatenate(([0], np.cumsum(lengths)))
+    total = int(offsets[-1])
+    seq = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=total)
+    if dirty:
+        for _ in range(total // 400):
+            p = int(rng.integers(0, total))
+            run = int(rng.integers(1, 40))
+            seq[p:p + run] = rng.choice(np.frombuffer(b"NnatgcRYKMSWU-*. ", dtype=np.uint8), size=len(seq[p:p + run]))
+    return seq, offsets
+
+
+@pytest.mark.parametrize("k", [4, 5, 6])
+@pytest.mark.parametrize("dirty", [False, True])
+def test_random_contigs_match_oracle(k, dirty):
+    from phamers_b200 import ops
+    rng = np.random.default_rng(100 * k + dirty)
+    seq, offsets = _random_workload(rng, 3000, dirty)
+    want = c_oracle.count(seq, offsets, k)
+    d_seq, d_off = _device(seq, offsets)
+    counts, freq = ops.count_cuda(d_seq, d_off, k, freq=True)
+    assert np.array_equal(_u32(counts), want)
+    want_freq = c_oracle.normalize(want)
+    assert np.array_equal(freq.cpu().numpy(), want_freq, equal_nan=True)
+    # canonical fold = the fixed linear fold of the oracle's 4^k vector
+    canon, _ = ops.count_cuda(d_seq, d_off, k, canonical=True)
+    assert np.array_equal(_u32(canon), po.canonical_fold(want, k))
+    # packed path
+    codes, valid = ops.pack_cuda(d_seq)
+    packed, _ = ops.count_packed_cuda(codes, valid, d_off, k)
+    assert np.array_equal(_u32(packed), want)
+
+
+def test_unaligned_offsets_and_single_long_contig():
+    from phamers_b200 import ops
+    rng = np.random.default_rng(5)
+    # contigs starting at every alignment, including empty ones between them
+    lengths = np.array([17, 0, 1, 3, 4, 5, 16, 15, 31, 33, 0, 64, 1000, 7, 511, 513, 2, 700001], dtype=np.int64)
+    offsets = np.concatenate(([0], np.cumsum(lengths)))
+    seq = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(offsets[-1]))
+    seq[offsets[-2] + 350000] = ord("N")
+    d_seq, d_off = _device(seq, offsets)
+    for k in (4, 5, 6):
+        counts, _ = ops.count_cuda(d_seq, d_off, k)
+        assert np.array_equal(_u32(counts), c_oracle.count(seq, offsets, k))
+
+
+def test_pack_format():
+    from phamers_b200 import ops
+    text = b"ATGCNatgcATGCATGCATGCATGCATGCATGCA-T"
+    d = torch.zeros((48,), dtype=torch.uint8)
+    d[:len(text)] = torch.tensor(list(text), dtype=torch.uint8)
+    codes, valid = ops.pack_cuda(d.cuda())
+    codes = codes.cpu().numpy().view(np.uint32)
+    valid = valid.cpu().numpy().view(np.uint32)
+    sym = {ord("A"): 0, ord("T"): 1, ord("G"): 2, ord("C"): 3}
+    padded = np.zeros(48, dtype=np.uint8)
+    padded[:len(text)] = np.frombuffer(text, dtype=np.uint8)
+    for i, c in enumerate(padded):
+        code = (int(codes[i // 16]) >> (30 - 2 * (i % 16))) & 3
+        ok = (int(valid[i // 32]) >> (31 - (i % 32))) & 1
+        assert ok == (1 if c in sym else 0), i
+        assert code == sym.get(int(c), 0), i
+
+
+def test_properties_at_scale():
+    """Size-independent checks on a device-generated workload: row sums equal L - k + 1 for clean contigs, the
+    stride-2 and stride-1 histograms and the simple kernel agree, canonical mass is conserved."""
+    from phamers_b200 import ops, _lib
+    seq, off = ops.synth_contigs(20260101, 0, 20000)
+    lengths = (off[1:] - off[:-1]).cpu().numpy()
+    assert lengths.min() >= 1000 and lengths.max() <= 100000
+    counts4, freq4 = ops.count_cuda(seq, off, 4, freq=True)
+    c4 = _u32(counts4)
+    assert np.array_equal(c4.sum(axis=1), lengths - 3)
+    assert np.allclose(freq4.sum(dim=1).cpu().numpy(), 1.0, atol=1e-12)
+    naive, _ = ops.count_cuda(seq, off, 4, naive=True)
+    assert torch.equal(naive, counts4)
+    _lib.set_option("hist_stride_k4", 1)
+    try:
+        s1, _ = ops.count_cuda(seq, off, 4)
+    finally:
+        _lib.set_option("hist_stride_k4", 2)
+    assert torch.equal(s1, counts4)
+    for k in (5, 6):
+        ck, _ = ops.count_cuda(seq, off, k)
+        assert np.array_equal(_u32(ck).sum(axis=1), lengths - k + 1)
+        # marginalising the last base of the k-mers gives the (k-1)-mers except the final window
+        canon, _ = ops.count_cuda(seq, off, k, canonical=True)
+        assert np.array_equal(_u32(canon).sum(axis=1), lengths - k + 1)
+    # a prefix against the oracle, byte for byte
+    n = 300
+    end = int(off[n].item())
+    host_seq = seq[:end].cpu().numpy()
+    host_off = off[:n + 1].cpu().numpy()
+    assert np.array_equal(c4[:n], c_oracle.count(host_seq, host_off, 4))
+    # determinism of the generator across shards
+    seq2, off2 = ops.synth_contigs(20260101, 100, 50)
+    a0, a1 = int(off[100].item()), int(off[150].item())
+    assert torch.equal(seq2, seq[a0:a1])
