@@ -262,6 +262,8 @@ def run_b200(args, rank, local_rank, world):
     elapsed_ms = float(t.item())
     all_bases = float(tot_bases.item())
 
+    score_stats = ops.score_stats() if (args.k == 4 and ops.score_path_option != 1) else None
+
     # ---- sanity inside the bench: row sums of the last step's counts (clean synthetic bases) ----
     lengths = offsets[1:] - offsets[:-1]
     assert bool((counts.sum(dim=1, dtype=torch.int64) == lengths - (args.k - 1)).all()), "count row sums are wrong"
@@ -312,7 +314,7 @@ def run_b200(args, rank, local_rank, world):
                   "traffic": None, "kernel": "kmer_hist_kernel", "peak_source": peaks["source"]}
     count_roof["frac"] = count_roof["achieved"] / count_roof["peak"]
     score_roof = {"bound": "tensor", "achieved": score_flops / (s_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
-                  "unit": "TFLOP/s", "traffic": None, "kernel": "score_exact_kernel (float64 CUDA cores, not tensor cores yet)",
+                  "unit": "TFLOP/s", "traffic": None, "kernel": "score_tc_kernel (tcgen05 kind::f16, 3 split-FP16 products per algorithmic product) + rerank_kernel",
                   "peak_source": peaks["source"]}
     score_roof["frac"] = score_roof["achieved"] / score_roof["peak"]
     dominant = count_roof if c_ms >= s_ms else score_roof
@@ -341,7 +343,8 @@ def run_b200(args, rank, local_rank, world):
                    "parallelism": "contigs sharded over %d GPU(s), references replicated, one NCCL all-gather of scores" % world,
                    "options": args.opt},
         "contigs_per_sec": n * world * args.steps / (elapsed_ms * 1e-3),
-        "kernels": {"count_ms": c_ms, "score_ms": s_ms, "count_roofline": count_roof, "score_roofline": score_roof},
+        "kernels": {"count_ms": c_ms, "score_ms": s_ms, "count_roofline": count_roof, "score_roofline": score_roof,
+                    "score_stats": score_stats},
         "roofline": dominant, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "device": {"sm": "%d.%d" % (caps.sm_major, caps.sm_minor), "sm_count": caps.sm_count},
     }

@@ -58,8 +58,10 @@ int64_t      phm_num_bins(int k, uint32_t flags);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  sequence pack.  Replaces kmer.sequence_to_integers (scripts/kmer.py:183-196): ASCII bases ->
- *     2-bit codes in reference order (A=0 T=1 G=2 C=3), 16 bases per uint32 (base i of a word in bits
- *     2i+1:2i), plus one validity bit per base, 32 bases per uint32 (bit i = base i is one of ATGC).
+ *     2-bit codes in reference order (A=0 T=1 G=2 C=3), 16 bases per uint32 with the FIRST base in the
+ *     top two bits (base i of a word in bits 31-2i:30-2i, so the bin of the k-mer starting at base i
+ *     is the plain bit field (word >> (32-2i-2k)) & (4^k-1)), plus one validity bit per base, 32 bases
+ *     per uint32, first base in the top bit (bit 31-i = base i is one of ATGC; codes of other bytes are 0).
  *     d_seq must be 16-byte aligned.  d_codes holds ceil(n_bases/16) words, d_valid ceil(n_bases/32).
  * ------------------------------------------------------------------------------------------- */
 int phm_pack_fasta(const uint8_t *d_seq, int64_t n_bases, uint32_t *d_codes, uint32_t *d_valid, void *stream);
@@ -107,6 +109,11 @@ int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, int64_t bins,
  *     d_kmeans        float64[n_points]  tanh((e_neg-e_pos)/(e_pos+e_neg))  (may be NULL)
  *     d_combo         float64[n_points]  knn + kmeans                     (may be NULL)
  *     A query row holding NaN (zero-count contig) gets NaN in all three outputs.
+ *
+ *     Two device paths, same results: for dim = 256 the (query x reference) contraction runs on the tcgen05 tensor
+ *     cores (split-FP16 operands, FP32 accumulation) to SHORTLIST 8 references + 4 centroids per class per query, the
+ *     shortlist is re-measured exactly in float64 and a margin test proves it complete; rows that fail the proof (and
+ *     every other shape) go through the exhaustive float64 kernel.  See DESIGN.md for the error bound.
  * ------------------------------------------------------------------------------------------- */
 size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg, int dim);
 int phm_score(const double *d_points, int64_t n_points, int dim,
@@ -114,6 +121,18 @@ int phm_score(const double *d_points, int64_t n_points, int dim,
               const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
               int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
               void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
+ * re-scored by the exhaustive float64 kernel because their shortlist margin proof failed, and the largest
+ * |ranking value - exact| squared-distance error seen on any re-ranked reference candidate: max_rank_error[0] absolute,
+ * max_rank_error[1] relative to |a|^2 + |b|^2 (both only collected while option "score_stats" is 1), max_rank_error[2] =
+ * rows whose mixed neighbour band was re-measured exactly.  The caller passes room for three floats. */
+int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max_rank_error, void *stream);
+
+/* Tuning / path selection for experiments and tests.  Options: "hist_stride_k4" (1 | 2), "hist_contigs_per_item",
+ * "score_path" (0 = tensor cores when the shape allows, 1 = exhaustive float64 only, 2 = tensor cores or error),
+ * "score_stats" (1 = collect ranking-error diagnostics, slower). */
+int phm_set_option(const char *name, int64_t value);
 
 /* ---------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only): contigs with lengths clip(round(exp(N(ln 10000, 1))), 1000,

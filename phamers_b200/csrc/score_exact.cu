@@ -10,7 +10,7 @@
 // margin check fails, and the tests use it to cross-check the tensor-core path at sizes the CPU oracle cannot reach.
 #include <math.h>
 
-#include "phm_common.cuh"
+#include "score_common.cuh"
 
 namespace phm {
 
@@ -34,18 +34,6 @@ __global__ void row_norms_kernel(const double *__restrict__ x, int64_t n_rows, i
         if (lane == 0) out[r] = s;
     }
 }
-
-struct ScoreArgs {
-    const double *points; int64_t n_points; int dim;
-    const double *refs; int64_t n_refs; int64_t n_positive;
-    const double *cent_pos; int64_t n_cent_pos;
-    const double *cent_neg; int64_t n_cent_neg;
-    const double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
-    const int64_t *row_list;      // optional: score only these rows (exact fallback of the tensor-core path)
-    int64_t n_rows;               // rows to score (= n_points when row_list is null)
-    int k_neighbors;
-    double *knn, *kmeans, *combo;
-};
 
 struct ExactSmem {
     double As[DK][TQ + 4];
@@ -87,12 +75,14 @@ __global__ void __launch_bounds__(256) score_exact_kernel(ScoreArgs a) {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t q0 = (int64_t)blockIdx.x * TQ;
+    const int64_t n_rows = a.n_rows_dev ? (int64_t)*a.n_rows_dev : a.n_rows;
+    if (q0 >= n_rows) return;
     const int64_t n_cols = a.n_refs + a.n_cent_pos + a.n_cent_neg;
     const int kn = a.k_neighbors;
 
     if (tid < TQ) {
         const int64_t r = q0 + tid;
-        qrow[tid] = (r < a.n_rows) ? (a.row_list ? a.row_list[r] : r) : -1;
+        qrow[tid] = (r < n_rows) ? (a.row_list ? a.row_list[r] : r) : -1;
         for (int j = 0; j <= KNN_MAX; ++j) { knn_d[tid][j] = INFINITY; knn_i[tid][j] = -1; }
         for (int j = 0; j < 4; ++j) { cen_d[tid][j] = INFINITY; cen_i[tid][j] = -1; }
     }
@@ -218,10 +208,18 @@ int launch_row_norms(const double *x, int64_t n_rows, int dim, double *out, cuda
 
 }  // namespace phm
 
+namespace phm { int score_path = 0; }
+
 using namespace phm;
 
-extern "C" size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg, int) {
-    return (size_t)(n_points + n_refs + n_cent_pos + n_cent_neg + 8) * sizeof(double);
+
+extern "C" size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg, int dim) {
+    const size_t exact = (size_t)(n_points + n_refs + n_cent_pos + n_cent_neg + 8) * sizeof(double);
+    if (dim == 256) {
+        const size_t tcb = tc::score_tc_workspace_bytes(n_points, n_refs, n_cent_pos, n_cent_neg);
+        return tcb > exact ? tcb : exact;
+    }
+    return exact;
 }
 
 extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
@@ -242,21 +240,35 @@ extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
         set_error("workspace too small");
         return PHM_E_WORKSPACE;
     }
-    double *ws = static_cast<double *>(d_workspace);
     ScoreArgs a;
     a.points = d_points; a.n_points = n_points; a.dim = dim;
     a.refs = d_refs; a.n_refs = n_refs; a.n_positive = n_positive;
     a.cent_pos = d_cent_pos; a.n_cent_pos = n_cent_pos;
     a.cent_neg = d_cent_neg; a.n_cent_neg = n_cent_neg;
-    double *np_ = ws, *nr = np_ + n_points, *ncp = nr + n_refs, *ncn = ncp + n_cent_pos;
-    a.norm_points = np_; a.norm_refs = nr; a.norm_cpos = ncp; a.norm_cneg = ncn;
-    a.row_list = nullptr; a.n_rows = n_points;
+    a.row_list = nullptr; a.n_rows_dev = nullptr; a.n_rows = n_points;
     a.k_neighbors = k_neighbors;
     a.knn = d_knn; a.kmeans = d_kmeans; a.combo = d_combo;
+
+    const bool tc_ok = tc::score_tc_supported(dim, k_neighbors, n_cent_pos, n_cent_neg);
+    if (score_path == 2 && !tc_ok) { set_error("tensor-core scoring needs dim = 256, k_neighbors <= 5 and both centroid sets"); return PHM_E_UNSUPPORTED; }
+    if (score_path != 1 && tc_ok) return tc::score_tc(a, d_workspace, workspace_bytes, st, nullptr);
+
+    double *ws = static_cast<double *>(d_workspace);
+    double *np_ = ws, *nr = np_ + n_points, *ncp = nr + n_refs, *ncn = ncp + n_cent_pos;
+    a.norm_points = np_; a.norm_refs = nr; a.norm_cpos = ncp; a.norm_cneg = ncn;
     int rc;
     if ((rc = launch_row_norms(d_points, n_points, dim, np_, st)) != PHM_OK) return rc;
     if ((rc = launch_row_norms(d_refs, n_refs, dim, nr, st)) != PHM_OK) return rc;
     if ((rc = launch_row_norms(d_cent_pos, n_cent_pos, dim, ncp, st)) != PHM_OK) return rc;
     if ((rc = launch_row_norms(d_cent_neg, n_cent_neg, dim, ncn, st)) != PHM_OK) return rc;
     return launch_score_exact(a, st);
+}
+
+// Diagnostics of the last tensor-core phm_score call that used this workspace (synchronises the stream).
+extern "C" int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max_rank_error, void *stream) {
+    PHM_REQUIRE(d_workspace && fallback_rows && max_rank_error, "null pointer");
+    unsigned long long fb = 0;                  // max_rank_error points at 3 floats: absolute, relative, rows re-measured
+    int rc = tc::score_tc_stats(d_workspace, &fb, max_rank_error, static_cast<cudaStream_t>(stream));
+    *fallback_rows = fb;
+    return rc;
 }

@@ -125,8 +125,31 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3):
                         ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
                         ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
     if n:
-        _launched(1 + sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]))
+        # both paths: 4 row-preparation kernels (when non-empty) + scorer; the tensor-core path adds re-rank + exact fallback
+        tc_path = dim == 256 and k_neighbors <= 5 and cent_pos.shape[0] and cent_neg.shape[0] and score_path_option != 1
+        _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (3 if tc_path else 1))
     return knn, kmeans, combo
+
+
+score_path_option = 0
+
+
+def set_score_path(path):
+    """'auto' (tensor cores when the shape allows), 'exact' (exhaustive float64), 'tc' (tensor cores or error)."""
+    global score_path_option
+    score_path_option = {"auto": 0, "exact": 1, "tc": 2}[path]
+    _lib.set_option("score_path", score_path_option)
+
+
+def score_stats():
+    """Diagnostics of the last tensor-core score_cuda call: rows re-scored by the exhaustive kernel, rows whose mixed
+    neighbour band was re-measured, and (with _lib.set_option('score_stats', 1)) the largest ranking error."""
+    lib = _lib.require_cuda()
+    ws = _workspaces[("score", torch.cuda.current_device())]
+    rows, err = ctypes.c_uint64(0), (ctypes.c_float * 3)()
+    check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
+    return {"fallback_rows": int(rows.value), "max_rank_error": float(err[0]), "max_rank_rel_error": float(err[1]),
+            "rows_remeasured": int(err[2])}
 
 
 def synth_contigs(seed, first_contig, n_contigs):

@@ -93,3 +93,47 @@ def test_nan_rows_score_nan(scoring):
     pts[1, :] = np.nan
     out = phamer.score_points(pts, pos, neg)
     assert np.isnan(out[1]) and np.isfinite(out[0]) and np.isfinite(out[2])
+
+
+def test_tensor_core_path_agrees_with_exact_path(scoring):
+    """The tcgen05 shortlist + float64 re-rank must give the same votes and the same scores (to rounding) as the
+    exhaustive float64 kernel, on the golden queries and on a larger mixed set; the margin proof should rarely fail."""
+    import torch
+    from phamers_b200 import _lib, kmer, ops, references
+    g, pos, neg = scoring
+    rng = np.random.default_rng(3)
+    _, pos_c, _, neg_c = references.load_reference_counts()
+    both = np.vstack((pos_c, neg_c)).astype(np.float64)
+    rows = []
+    for _ in range(3000):
+        row = both[int(rng.integers(0, both.shape[0]))]
+        rows.append(rng.multinomial(int(rng.choice([3000, 16000, 100000])), row / row.sum()))
+    rows.extend(list(rng.integers(0, 120, size=(1500, 256))))
+    rows.extend(list(g["query_counts"]))
+    counts = np.stack(rows).astype(np.int64)
+    counts[7, :] = 0                                                      # one empty contig -> NaN row
+    pts = torch.from_numpy(kmer.normalize_counts(counts)).cuda()
+    refs = torch.from_numpy(np.vstack((pos, neg))).cuda()
+    cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
+    cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
+    try:
+        ops.set_score_path("exact")
+        e_knn, e_km, e_combo = [t.cpu().numpy() for t in ops.score_cuda(pts, refs, len(pos), cp, cn, 3)]
+        ops.set_score_path("tc")
+        _lib.set_option("score_stats", 1)
+        t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(pts, refs, len(pos), cp, cn, 3)]
+        stats = ops.score_stats()
+    finally:
+        _lib.set_option("score_stats", 0)
+        ops.set_score_path("auto")
+    assert np.isnan(t_combo[7]) and np.isnan(e_combo[7])
+    ok = ~np.isnan(e_combo)
+    assert np.array_equal(t_knn[ok], e_knn[ok])
+    assert np.max(np.abs(t_km[ok] - e_km[ok])) <= 1e-12
+    assert np.max(np.abs(t_combo[ok] - e_combo[ok])) <= 1e-12
+    n_gold = len(g["query_counts"])
+    assert np.array_equal(t_knn[-n_gold:], g["scores_knn"])
+    assert np.max(np.abs(t_combo[-n_gold:] - g["scores_combo"])) <= TOL
+    print("tensor-core path on %d rows: %s" % (len(counts), stats))
+    assert stats["fallback_rows"] <= len(counts) // 10
+    assert stats["max_rank_rel_error"] < 2.0 ** -16          # the bound used is 2^-15
