@@ -39,12 +39,11 @@ namespace tc {
 constexpr int KDIM = 256;                 // feature width handled by this kernel (k = 4)
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int NKC = KDIM / BK;            // 4 K-chunks of 128 bytes
-constexpr int NSTAGE = 5;                 // ring of single operand blocks: hi(kc), lo(kc), hi(kc+1), ...
+constexpr int NSTAGE = 4;                 // ring of single operand blocks: hi(kc), lo(kc), hi(kc+1), ...
 constexpr int BLOCK_BYTES = BM * BK * 2;  // 16 KB: 128 rows x 128 B
 constexpr int A_BYTES = 2 * NKC * BLOCK_BYTES;          // hi + lo
 constexpr int NGROUP = 2;                 // epilogue warp groups (4 warps each); group g owns reference tiles with tile % 2 == g
-constexpr int STACK_CAP = 8;              // deferred candidates per thread between two shortlist merges
-constexpr int STACK_BYTES = NGROUP * 4 * 32 * STACK_CAP * 8;   // 8-byte slots (low word used)
+constexpr int STACK_BYTES = NGROUP * 4 * 32 * 32 * 4;   // per epilogue warp: 32 ranking values of each of its 32 rows
 constexpr int SMEM_EXTRA = 2048;
 constexpr int SMEM_BYTES = A_BYTES + NSTAGE * BLOCK_BYTES + STACK_BYTES + SMEM_EXTRA + 1024;   // + alignment slack
 constexpr int NTHREADS = 64 + NGROUP * 128;
@@ -136,73 +135,46 @@ __device__ __forceinline__ void shortlist_insert(float (&w)[L], int (&id)[L], fl
     w[0] = first ? v : w[0];
 }
 
-// One reference tile (128 columns) for this thread's contig row.  Values that beat the current threshold are pushed on a
-// small per-thread stack in shared memory (their column offsets go to a bit mask) and merged into the sorted shortlist once
-// per 32 columns: the divergent ~35-instruction insertion then runs max-over-lanes times per chunk instead of once per
-// candidate column.  Columns where no lane has a candidate cost three instructions (compare, vote, branch).  A thread that
-// finds more than STACK_CAP candidates in a chunk (first tiles of a contig tile only) merges what it has and re-examines
-// the remaining columns against the tightened threshold.
-template <bool FIRST>
-__device__ __forceinline__ void push_pass(const float (&v)[32], float limit, uint32_t pend, uint32_t stack_addr,
-                                          uint32_t &mask, uint32_t &over) {
-    uint32_t addr = stack_addr;
-    const uint32_t end = stack_addr + 256u * STACK_CAP;
-    mask = 0u;
-    over = 0u;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        bool c = v[i] < limit;
-        if (!FIRST) c = c && ((pend >> i) & 1u);
-        if (__any_sync(FULL, c)) {
-            if (c) {
-                if (addr != end) {
-                    sts_u32(addr, __float_as_uint(v[i]));
-                    addr += 256u;
-                    mask |= 1u << i;
-                } else {
-                    over |= 1u << i;
-                }
-            }
-        }
-    }
-}
-
+// One reference tile (128 columns) for this thread's contig row, CW columns at a time: the ranking values are formed
+// branch-free (tcgen05.ld, |b|^2 - acc), parked in shared memory, and the sign bits of (value - threshold) are funnelled
+// into a per-thread column mask.  Only then does the thread walk its set bits and merge those values into the sorted
+// shortlist, so the divergent ~35-instruction insertion runs max-over-lanes(popcount) times per chunk instead of once per
+// candidate column, and everything before it is straight-line code with instruction-level parallelism.
 template <int L>
-__device__ __forceinline__ void merge_stack(uint32_t stack_addr, uint32_t mask, int col, float (&w)[L], int (&id)[L]) {
-    const int cnt = __popc(mask);
-    const int rounds = __reduce_max_sync(FULL, cnt);
-    for (int r = 0; r < rounds; ++r) {
-        if (r < cnt) {
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            shortlist_insert<L>(w, id, __uint_as_float(lds_u32(stack_addr + 256u * r)), col + i);
-        }
-    }
-}
-
-template <int L>
-__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t stack_addr, int col0,
+__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t vbuf_addr, int col0,
                                           float (&w)[L], int (&id)[L]) {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
         float v[32];
         __syncwarp();                                  // tcgen05.ld is .sync.aligned: the warp must be converged
         tmem_ld32(taddr + (uint32_t)c, v);
+        const float limit = w[L - 1];
+        uint32_t h[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const uint4 nb = lds_v4(nbs_addr + 4u * (c + i));
-            v[i] = __uint_as_float(nb.x) - v[i];
-            v[i + 1] = __uint_as_float(nb.y) - v[i + 1];
-            v[i + 2] = __uint_as_float(nb.z) - v[i + 2];
-            v[i + 3] = __uint_as_float(nb.w) - v[i + 3];
+        for (int g = 0; g < 8; ++g) {
+            const uint4 nb = lds_v4(nbs_addr + 4u * (c + 4 * g));
+            float4 x;
+            x.x = __uint_as_float(nb.x) - v[4 * g];
+            x.y = __uint_as_float(nb.y) - v[4 * g + 1];
+            x.z = __uint_as_float(nb.z) - v[4 * g + 2];
+            x.w = __uint_as_float(nb.w) - v[4 * g + 3];
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(vbuf_addr + 512u * g), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+            // shift the sign of (value - limit) into the mask: first column of the chunk ends up in the top bit
+            uint32_t &m = h[g >> 1];
+            m = __funnelshift_l(__float_as_uint(x.x - limit), m, 1);
+            m = __funnelshift_l(__float_as_uint(x.y - limit), m, 1);
+            m = __funnelshift_l(__float_as_uint(x.z - limit), m, 1);
+            m = __funnelshift_l(__float_as_uint(x.w - limit), m, 1);
         }
-        uint32_t mask, over;
-        push_pass<true>(v, w[L - 1], 0xFFFFFFFFu, stack_addr, mask, over);
-        merge_stack<L>(stack_addr, mask, col0 + c, w, id);
-        while (__any_sync(FULL, over != 0u)) {
-            const uint32_t pend = over;
-            push_pass<false>(v, w[L - 1], pend, stack_addr, mask, over);
-            merge_stack<L>(stack_addr, mask, col0 + c, w, id);
+        uint32_t hits = (h[0] << 24) | (h[1] << 16) | (h[2] << 8) | h[3];
+        const int rounds = __reduce_max_sync(FULL, (unsigned)__popc(hits));
+        for (int r = 0; r < rounds; ++r) {
+            if (hits) {
+                const int i = __clz(hits);
+                hits &= ~(0x80000000u >> i);
+                const float x = __uint_as_float(lds_u32(vbuf_addr + 512u * (i >> 2) + 4u * (i & 3)));
+                if (x < w[L - 1]) shortlist_insert<L>(w, id, x, col0 + c + i);
+            }
         }
     }
 }
@@ -223,7 +195,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sm_a = smem_base;                                   // [hi chunk 0..3][lo chunk 0..3]
     const uint32_t sm_b = smem_base + A_BYTES;                         // NSTAGE operand blocks
-    const uint32_t sm_stack = sm_b + NSTAGE * BLOCK_BYTES;             // per epilogue warp: [STACK_CAP][32 lanes] x 8 bytes
+    const uint32_t sm_stack = sm_b + NSTAGE * BLOCK_BYTES;             // per epilogue warp: [8 column quads][32 lanes] x 16 bytes
     const uint32_t sm_x = sm_stack + STACK_BYTES;                      // barriers, tmem pointer, norm staging
     const uint32_t bar_a_full = sm_x + 0, bar_a_empty = sm_x + 8;
     const uint32_t bar_b_full = sm_x + 16, bar_b_empty = sm_x + 16 + 8 * NSTAGE;
@@ -316,7 +288,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
         const int group = (warp - 2) >> 2;                         // owns reference tiles with (tile & 1) == group
         const int epi_tid = ((warp - 2) & 3) * 32 + lane;          // 0..127 inside the group
-        const uint32_t stack_addr = sm_stack + (uint32_t)(warp - 2) * (32 * STACK_CAP * 8) + 8u * lane;
+        const uint32_t stack_addr = sm_stack + (uint32_t)(warp - 2) * 4096u + 16u * lane;
         const uint32_t nbs_addr = sm_nbs + (uint32_t)group * (BN * 4);
         for (int mt = blockIdx.x, it = 0; mt < p.n_mtiles; mt += gridDim.x, ++it) {
             float wr[LREF], wp[LCEN], wn[LCEN];
