@@ -110,10 +110,11 @@ int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, int64_t bins,
  *     d_combo         float64[n_points]  knn + kmeans                     (may be NULL)
  *     A query row holding NaN (zero-count contig) gets NaN in all three outputs.
  *
- *     Two device paths, same results: for dim = 256 the (query x reference) contraction runs on the tcgen05 tensor
- *     cores (split-FP16 operands, FP32 accumulation) to SHORTLIST 8 references + 4 centroids per class per query, the
- *     shortlist is re-measured exactly in float64 and a margin test proves it complete; rows that fail the proof (and
- *     every other shape) go through the exhaustive float64 kernel.  See DESIGN.md for the error bound.
+ *     Two device paths, same results: for dim = 256 and k_neighbors in {1, 3, 5} the (query x reference) contraction runs on
+ *     the tcgen05 tensor cores (FP16 operands, FP32 accumulation) together with a proven per-pair error interval; the few
+ *     references / centroids whose interval can reach the k nearest are kept per query and decided exactly in float64.
+ *     Rows whose candidate buffer overflows (and every other shape) go through the exhaustive float64 kernel.
+ *     See DESIGN.md section 5 for the error bound.
  * ------------------------------------------------------------------------------------------- */
 size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg, int dim);
 int phm_score(const double *d_points, int64_t n_points, int dim,
@@ -123,10 +124,10 @@ int phm_score(const double *d_points, int64_t n_points, int dim,
               void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
- * re-scored by the exhaustive float64 kernel because their shortlist margin proof failed, and the largest
- * |ranking value - exact| squared-distance error seen on any re-ranked reference candidate: max_rank_error[0] absolute,
- * max_rank_error[1] relative to |a|^2 + |b|^2 (both only collected while option "score_stats" is 1), max_rank_error[2] =
- * rows whose mixed neighbour band was re-measured exactly.  The caller passes room for three floats. */
+ * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
+ * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option
+ * "score_stats" is 1), stats[1] = largest |ranking value - exact| in squared-distance units (same condition), stats[2] =
+ * rows whose neighbour vote needed exact re-measurement.  The caller passes room for three floats. */
 int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max_rank_error, void *stream);
 
 /* Tuning / path selection for experiments and tests.  Options: "hist_stride_k4" (1 | 2), "hist_contigs_per_item",

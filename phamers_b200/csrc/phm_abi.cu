@@ -37,6 +37,7 @@ extern int hist_stride_for_k4;
 extern int hist_contigs_per_item;
 extern int score_path;
 extern int score_collect_stats;
+extern int score_debug;
 
 }  // namespace phm
 
@@ -71,6 +72,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_stride_k4")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k4 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 1 && value <= 4096, "1..4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_path")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 auto, 1 exact, 2 tensor cores"); score_path = (int)value; return PHM_OK; }
+    if (!strcmp(name, "score_debug")) { score_debug = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_stats")) { score_collect_stats = value != 0; return PHM_OK; }
     set_error("unknown option '%s'", name);
     return PHM_E_ARG;

@@ -21,7 +21,7 @@ int launch_score_exact(const ScoreArgs &a, cudaStream_t st);
 int launch_row_norms(const double *x, int64_t n_rows, int dim, double *out, cudaStream_t st);
 
 namespace tc {
-bool score_tc_supported(int dim, int k_neighbors, int64_t n_cent_pos, int64_t n_cent_neg);
+bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg);
 size_t score_tc_workspace_bytes(int64_t n_points, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg);
 int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int *kernels_launched);
 int score_tc_stats(const void *ws, unsigned long long *fallback_rows, float *max_rank_error, cudaStream_t st);

@@ -6,8 +6,8 @@
 // from a register-tiled x.y; the k nearest references vote, the two best centroids of each class are re-measured by
 // direct difference (as np.linalg.norm(point - centroid) does) and the nearer one enters tanh((e_n - e_p)/(e_p + e_n)).
 //
-// This kernel is the always-correct path: the tensor-core scorer (score_tc.cu) uses it for the rows whose shortlist
-// margin check fails, and the tests use it to cross-check the tensor-core path at sizes the CPU oracle cannot reach.
+// This kernel is the always-correct path: the tensor-core scorer (score_tc.cu) uses it for the rows whose candidate
+// buffer overflows, and the tests use it to cross-check the tensor-core path at sizes the CPU oracle cannot reach.
 #include <math.h>
 
 #include "score_common.cuh"
@@ -249,8 +249,8 @@ extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
     a.k_neighbors = k_neighbors;
     a.knn = d_knn; a.kmeans = d_kmeans; a.combo = d_combo;
 
-    const bool tc_ok = tc::score_tc_supported(dim, k_neighbors, n_cent_pos, n_cent_neg);
-    if (score_path == 2 && !tc_ok) { set_error("tensor-core scoring needs dim = 256, k_neighbors <= 5 and both centroid sets"); return PHM_E_UNSUPPORTED; }
+    const bool tc_ok = tc::score_tc_supported(dim, k_neighbors, n_refs, n_cent_pos, n_cent_neg);
+    if (score_path == 2 && !tc_ok) { set_error("tensor-core scoring needs dim = 256, k_neighbors in {1, 3, 5} and both centroid sets"); return PHM_E_UNSUPPORTED; }
     if (score_path != 1 && tc_ok) return tc::score_tc(a, d_workspace, workspace_bytes, st, nullptr);
 
     double *ws = static_cast<double *>(d_workspace);

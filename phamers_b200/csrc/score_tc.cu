@@ -1,29 +1,40 @@
-// K4 + K5 on the 5th-generation tensor cores: contig x reference distance contraction with a fused shortlist epilogue,
-// followed by an exact float64 re-rank.
+// K4 + K5 on the 5th-generation tensor cores: contig x reference distance contraction with a fused candidate-selection
+// epilogue, followed by an exact float64 decision kernel.
 //
 // Replaces learning.knn (reference scripts/learning.py:118-128), the per-contig nearest-centroid loop
 // (scripts/phamer.py:251-255 -> learning.closest_to :59-66) and proximity_metric (scripts/phamer.py:198-210).
 //
 //   d2(a, b) = |a|^2 + |b|^2 - 2 a.b          a = contig features [n, 256], b = reference rows / centroids
 //
-// The a.b term is a dense contraction and runs as tcgen05.mma (kind::f16, FP32 accumulators in tensor memory).  A single
-// FP16 pass is not accurate enough to rank neighbours (nearest-neighbour d2 ~ 2e-5 against |x|^2 ~ 5e-3),
-// so every operand is split into two FP16 terms of a 2^12-scaled value (x = hi + lo, 22 significant bits) and the product is
-// accumulated as hi.hi + hi.lo + lo.hi in the SAME accumulator (the dropped lo.lo term is 2^-22 relative).  With FP32
-// accumulation over 3 x 256 products the error of the ranking value is below 2^-15 (|a|^2 + |b|^2) (measured 2^-17.3, see
-// rerank_kernel); it is used for SHORTLIST SELECTION ONLY.  The epilogue keeps, straight out of tensor memory, the 8 best
-// references and the 4 best centroids of each class per contig; rerank_kernel then decides the vote from the error band
-// around the k-th ranking value, re-measures exactly (float64, direct difference) whatever the band leaves open plus the
-// nearest centroids, and evaluates tanh((e_n - e_p)/(e_p + e_n)).  Rows whose band reaches the end of the shortlist are
-// appended to a list and re-scored by the exhaustive float64 kernel (score_exact.cu).
+// The a.b term is a dense contraction and runs as ONE tcgen05.mma pass (kind::f16, FP32 accumulators in tensor memory) over
+// operands that are centred by 1/256 (distances are translation invariant), scaled by 2^12 and rounded to FP16.  FP16 x FP16
+// products are exact in FP32, so the only errors are the operand roundings and the FP32 accumulation; both are BOUNDED, per
+// (contig, reference) pair, by quantities that are computed exactly when the operands are prepared:
 //
-// Kernel layout (one CTA per SM, persistent over 128-contig tiles, 6 warps):
-//   warp 0    TMA producer   A tile (128 contigs x 256 features, hi + lo, 128 KB, SWIZZLE_128B) once per contig tile;
-//                            B stages (128 references x 64 features, hi + lo, 32 KB) through a 3-deep mbarrier ring
-//   warp 1    MMA issuer     one elected lane: 12 tcgen05.mma (128x128x16) per stage, 48 per reference tile, into one of two
-//                            128-column accumulators; tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-5 epilogue       tcgen05.ld 32 columns at a time, v = |b|^2 * 2^23 - acc, branch-free sorted insertion into the
-//                            per-thread shortlists (thread = contig row = tensor-memory lane)
+//     A = fp16(A~), A~ = 2^12 (a - 1/256)   dA = |A~ - A|_2 , nA = |A|_2          (per contig)
+//     B = fp16(B~), B~ = 2^12 (b - 1/256)   dB = |B~ - B|_2 , P  = |B~|_2         (per reference)
+//     A~.B~ - A.B = (A~ - A).B~ + A.(B~ - B)         =>   |A~.B~ - acc| <= dA P + nA dB + eps_acc nA (P + dB)
+//
+// (Cauchy-Schwarz; eps_acc = 2^-16 covers 16 FP32-accumulated MMAs, measured usage of the whole bound <= 0.4.)  With
+// rho = max_j (dB_j + eps_acc (P_j + dB_j)) / P_j over the reference set this collapses to   err_j <= C_row * P_j  with ONE
+// constant per contig row.  The ranking value x_j = 2^23 |b_j - u|^2 - acc_j therefore pins the exact value inside
+// [lo_j, up_j] = [x_j - C P_j, x_j + C P_j].  A reference can be one of the k nearest only if lo_j <= (k-th smallest up);
+// the epilogue keeps exactly those (they are few: the interval is ~1 % of the distance), straight out of tensor memory, and
+// score_decide_kernel reads the vote off them when it is already decided, or re-measures them in float64 by direct
+// difference.  Centroid distances that enter tanh((e_n - e_p)/(e_p + e_n)) are always exact float64.  A row whose candidate
+// buffer overflows is re-scored exhaustively in float64 (score_fallback_kernel).  The results are therefore those of exact
+// arithmetic; the tensor cores only decide WHICH handful of the R references need to be looked at.
+//
+// Kernel layout (one CTA per SM, persistent over 256-contig tiles, 10 warps):
+//   warp 0    TMA producer   A tile (256 contigs x 256 features FP16, 128 KB, SWIZZLE_128B) once per contig tile;
+//                            B blocks (128 references x 64 features, 16 KB) through a 4-deep mbarrier ring
+//   warp 1    MMA issuer     one elected lane: per B block 2 x 4 tcgen05.mma (128x128x16), i.e. two 128-row halves share every
+//                            B block, into one of two 2 x 128-column accumulator sets (all 512 TMEM columns);
+//                            tcgen05.commit frees the block / publishes the accumulator set
+//   warps 2-9 epilogue       thread = contig row = tensor-memory lane.  32 columns per tcgen05.ld (next load in flight while
+//                            the current one is scanned): lo_j = fma(-C, P_j, nbs_j - acc_j), running minimum; only when some
+//                            lane's minimum beats its threshold are the hits examined (bit mask, then per hit: k smallest
+//                            upper bounds in registers + append to the row's candidate buffer in shared memory)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -32,30 +43,34 @@
 
 namespace phm {
 
-int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record the ranking error
+int score_debug = 0;              // option "score_debug": timing experiments only (1 = epilogue skips the scan, 2 = scan without hits)
+int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record how much of the bound is used
 
 namespace tc {
 
 constexpr int KDIM = 256;                 // feature width handled by this kernel (k = 4)
 constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int MT = 2 * BM;                // contig rows per CTA tile (two MMA row blocks share every B block)
 constexpr int NKC = KDIM / BK;            // 4 K-chunks of 128 bytes
-constexpr int NSTAGE = 4;                 // ring of single operand blocks: hi(kc), lo(kc), hi(kc+1), ...
+constexpr int NSTAGE = 4;                 // ring of B blocks
 constexpr int BLOCK_BYTES = BM * BK * 2;  // 16 KB: 128 rows x 128 B
-constexpr int A_BYTES = 2 * NKC * BLOCK_BYTES;          // hi + lo
-constexpr int NGROUP = 2;                 // epilogue warp groups (4 warps each); group g owns reference tiles with tile % 2 == g
-constexpr int STACK_BYTES = NGROUP * 4 * 32 * 32 * 4;   // per epilogue warp: 32 ranking values of each of its 32 rows
-constexpr int SMEM_EXTRA = 2048;
-constexpr int SMEM_BYTES = A_BYTES + NSTAGE * BLOCK_BYTES + STACK_BYTES + SMEM_EXTRA + 1024;   // + alignment slack
-constexpr int NTHREADS = 64 + NGROUP * 128;
-constexpr int TMEM_COLS = 256;            // two 128-column FP32 accumulators
-constexpr int LREF = 8;                   // shortlist of references per contig and epilogue group
-constexpr int LCEN = 4;                   // shortlist of centroids per class
-constexpr int NSLOT = LREF + 2 * LCEN;    // 16 candidate slots per group
-constexpr int NCAND = NGROUP * NSLOT;     // 32 per contig
-constexpr float SCALE = 4096.0f;          // operands are scaled by 2^12 -> accumulator = 2^24 a.b
-constexpr float NORM_SCALE = 8388608.0f;  // 2^23: v = 2^23 (|b|^2 - 2 a.b)
+constexpr int A_BYTES = 2 * NKC * BLOCK_BYTES;          // [half][kc]
+constexpr int NEPI = MT;                  // epilogue threads (one per contig row of the tile)
+constexpr int CAP_R = 10;                 // candidate slots per row: references
+constexpr int CAP_C = 3;                  //                          centroids of one class
+constexpr int NENT = CAP_R + 2 * CAP_C;   // 16 entries of 8 bytes per row
+constexpr int CAND_BYTES = NEPI * NENT * 8;
+constexpr int STG_BYTES = 2 * 2 * BN * 4; // [accumulator set][nbs | P][128 columns] floats
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = A_BYTES + NSTAGE * BLOCK_BYTES + CAND_BYTES + STG_BYTES + BAR_BYTES;
+constexpr int NTHREADS = 64 + NEPI;
+constexpr int TMEM_COLS = 512;            // two sets of (2 halves x 128 columns) FP32 accumulators
+constexpr float SCALE = 4096.0f;          // operands are scaled by 2^12 -> accumulator = 2^24 a'.b'
+constexpr double NORM_SCALE = 8388608.0;  // 2^23: ranking value = 2^23 (|b'|^2 - 2 a'.b')
 constexpr float PAD_NORM = 3.0e38f;
+constexpr double EPS_ACC = 1.0 / 65536.0; // FP32 accumulation allowance relative to |A| |B|
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // F16 x F16 -> F32, K-major
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
 
 // ---------------- PTX helpers ----------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -83,6 +98,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {                  // true in exactly one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -104,115 +128,230 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 consecutive accumulator columns of this thread's row; the result registers are valid after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
 
-// branch-free sorted insertion (ascending, ties keep the earlier entry)
-template <int L>
-__device__ __forceinline__ void shortlist_insert(float (&w)[L], int (&id)[L], float v, int j) {
+// ---------------- epilogue building blocks ----------------
+// k smallest upper bounds seen so far, ascending; u[K-1] is the row's threshold
+template <int K>
+__device__ __forceinline__ void upper_insert(float (&u)[K], float v) {       // 2K min/max, branch-free
 #pragma unroll
-    for (int i = L - 1; i > 0; --i) {
-        const bool shift = v < w[i - 1];
-        const bool here = v < w[i];
-        id[i] = shift ? id[i - 1] : (here ? j : id[i]);
-        w[i] = shift ? w[i - 1] : (here ? v : w[i]);
+    for (int i = 0; i < K; ++i) {
+        const float keep = fminf(u[i], v);
+        v = fmaxf(u[i], v);
+        u[i] = keep;
     }
-    const bool first = v < w[0];
-    id[0] = first ? j : id[0];
-    w[0] = first ? v : w[0];
 }
 
-// One reference tile (128 columns) for this thread's contig row, CW columns at a time: the ranking values are formed
-// branch-free (tcgen05.ld, |b|^2 - acc), parked in shared memory, and the sign bits of (value - threshold) are funnelled
-// into a per-thread column mask.  Only then does the thread walk its set bits and merge those values into the sorted
-// shortlist, so the divergent ~35-instruction insertion runs max-over-lanes(popcount) times per chunk instead of once per
-// candidate column, and everything before it is straight-line code with instruction-level parallelism.
-template <int L>
-__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t vbuf_addr, int col0,
-                                          float (&w)[L], int (&id)[L]) {
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        __syncwarp();                                  // tcgen05.ld is .sync.aligned: the warp must be converged
-        tmem_ld32(taddr + (uint32_t)c, v);
-        const float limit = w[L - 1];
-        uint32_t h[4] = {0u, 0u, 0u, 0u};
+// Candidate buffer of one row: entries `first` .. `first + CAP - 1` of the thread's 16 slots; entry e of thread t lives at
+// cand_addr + e * (NEPI * 8) (cand_addr already holds the thread's 8-byte column, so a warp touches 256 contiguous bytes).
+template <int CAP>
+__device__ __forceinline__ void cand_prune(uint32_t cand_addr, int first, int &cnt, float limit) {
+    int w = 0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const uint4 nb = lds_v4(nbs_addr + 4u * (c + 4 * g));
-            float4 x;
-            x.x = __uint_as_float(nb.x) - v[4 * g];
-            x.y = __uint_as_float(nb.y) - v[4 * g + 1];
-            x.z = __uint_as_float(nb.z) - v[4 * g + 2];
-            x.w = __uint_as_float(nb.w) - v[4 * g + 3];
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(vbuf_addr + 512u * g), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-            // shift the sign of (value - limit) into the mask: first column of the chunk ends up in the top bit
-            uint32_t &m = h[g >> 1];
-            m = __funnelshift_l(__float_as_uint(x.x - limit), m, 1);
-            m = __funnelshift_l(__float_as_uint(x.y - limit), m, 1);
-            m = __funnelshift_l(__float_as_uint(x.z - limit), m, 1);
-            m = __funnelshift_l(__float_as_uint(x.w - limit), m, 1);
-        }
-        uint32_t hits = (h[0] << 24) | (h[1] << 16) | (h[2] << 8) | h[3];
-        const int rounds = __reduce_max_sync(FULL, (unsigned)__popc(hits));
-        for (int r = 0; r < rounds; ++r) {
-            if (hits) {
-                const int i = __clz(hits);
-                hits &= ~(0x80000000u >> i);
-                const float x = __uint_as_float(lds_u32(vbuf_addr + 512u * (i >> 2) + 4u * (i & 3)));
-                if (x < w[L - 1]) shortlist_insert<L>(w, id, x, col0 + c + i);
-            }
+    for (int e = 0; e < CAP; ++e) {
+        const uint2 ent = lds_v2(cand_addr + (uint32_t)(first + e) * (NEPI * 8));
+        if (e < cnt && __uint_as_float(ent.x) <= limit) {
+            sts_v2(cand_addr + (uint32_t)(first + w) * (NEPI * 8), ent.x, ent.y);
+            ++w;
         }
     }
+    cnt = w;
+}
+
+template <int CAP>
+__device__ __forceinline__ void cand_append(uint32_t cand_addr, int first, int &cnt, bool &overflow, float limit, float lo, int col) {
+    if (cnt == CAP) cand_prune<CAP>(cand_addr, first, cnt, limit);
+    if (cnt == CAP) {
+        overflow = true;                        // more live candidates than slots: the row goes to the exhaustive kernel
+    } else {
+        sts_v2(cand_addr + (uint32_t)(first + cnt) * (NEPI * 8), __float_as_uint(lo), (uint32_t)col);
+        ++cnt;
+    }
+}
+
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // v[j] for a warp-uniform j
+    switch (j) {
+#define PHM_PICK(i) case i: return v[i];
+        PHM_PICK(0) PHM_PICK(1) PHM_PICK(2) PHM_PICK(3) PHM_PICK(4) PHM_PICK(5) PHM_PICK(6) PHM_PICK(7)
+        PHM_PICK(8) PHM_PICK(9) PHM_PICK(10) PHM_PICK(11) PHM_PICK(12) PHM_PICK(13) PHM_PICK(14) PHM_PICK(15)
+        PHM_PICK(16) PHM_PICK(17) PHM_PICK(18) PHM_PICK(19) PHM_PICK(20) PHM_PICK(21) PHM_PICK(22) PHM_PICK(23)
+        PHM_PICK(24) PHM_PICK(25) PHM_PICK(26) PHM_PICK(27) PHM_PICK(28) PHM_PICK(29) PHM_PICK(30)
+#undef PHM_PICK
+        default: return v[31];
+    }
+}
+
+// 32 accumulator columns of this thread's row (already in registers): lower bounds and their minimum against the row's
+// threshold; only if some lane of the warp has a hit are the hits looked at, one warp-uniform column at a time.
+// INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
+template <int K, int CAP, bool INSERT>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
+                                           int n_class, float C, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
+                                           bool &overflow) {
+    float lo[32], gm[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const uint4 nb = lds_v4(nbs_c + 16u * g);
+        const uint4 pp = lds_v4(p_c + 16u * g);
+        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]));
+        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]));
+        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]));
+        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]));
+        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
+    }
+    const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+    const float limit0 = u[K - 1];
+    if (!__any_sync(FULL, m <= limit0)) return;
+
+    // sign of (limit - lo) shifted in column by column: column 0 ends in the top bit, a clear bit is a hit (lo <= limit)
+    uint32_t mq[4] = {0u, 0u, 0u, 0u};                   // four independent chains of 8 columns
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mq[c] = __funnelshift_l(__float_as_uint(limit0 - lo[8 * c + j]), mq[c], 1);
+    const uint32_t miss = (mq[0] << 24) | ((mq[1] & 255u) << 16) | ((mq[2] & 255u) << 8) | (mq[3] & 255u);
+    const uint32_t hits = __brev(~miss);
+    // make room once for the whole warp (one uniform pass) instead of lane by lane inside the loop
+    if (__any_sync(FULL, cnt + __popc(hits) > CAP)) cand_prune<CAP>(cand_addr, first, cnt, limit0);
+    uint32_t todo = __reduce_or_sync(FULL, hits);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float lo_j = pick32(lo, j);
+        if (((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
+            if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(lds_u32(p_c + 4u * j)), lo_j));
+            cand_append<CAP>(cand_addr, first, cnt, overflow, u[K - 1], lo_j, col_c + j);
+        }
+    }
+}
+
+// First pass of a two-pass tile: every column's upper bound goes through the branch-free insertion network, so that the
+// threshold is already tight when the hits are collected (scan_chunk<.., false> over the same accumulators).
+template <int K>
+__device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, float C, float (&u)[K]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const uint4 nb = lds_v4(nbs_c + 16u * g);
+        const uint4 pp = lds_v4(p_c + 16u * g);
+        const float nbv[4] = {__uint_as_float(nb.x), __uint_as_float(nb.y), __uint_as_float(nb.z), __uint_as_float(nb.w)};
+        const float ppv[4] = {__uint_as_float(pp.x), __uint_as_float(pp.y), __uint_as_float(pp.z), __uint_as_float(pp.w)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float lo = fmaf(-C, ppv[i], nbv[i] - __uint_as_float(r[4 * g + i]));
+            upper_insert<K>(u, fmaf(2.0f * C, ppv[i], lo));
+        }
+    }
+}
+
+// One tile (128 columns) of this thread's row: four 32-column loads, the next one in flight while one is scanned.
+// TWO_PASS (first reference tile of a contig tile, centroid tiles): thresholds start at +inf there, so nearly every column
+// would be a hit; instead all 128 upper bounds go through the insertion network first and the hits are collected in a second
+// sweep over the same accumulators (they stay in tensor memory until the set is released).
+template <int K, int CAP, bool TWO_PASS>
+__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C,
+                                          uint32_t cand_addr, int first, float (&u)[K], int &cnt, bool &overflow) {
+    uint32_t ra[32], rb[32];
+    __syncwarp();                                      // tcgen05.ld is .sync.aligned: the warp must be converged
+    tmem_ld32_issue(taddr, ra);
+    tmem_wait_ld();
+    if (TWO_PASS) {
+        tmem_ld32_issue(taddr + 32u, rb);
+        bound_chunk<K>(ra, nbs_addr, p_addr, C, u);
+        tmem_wait_ld();
+        tmem_ld32_issue(taddr + 64u, ra);
+        bound_chunk<K>(rb, nbs_addr + 128u, p_addr + 128u, C, u);
+        tmem_wait_ld();
+        tmem_ld32_issue(taddr + 96u, rb);
+        bound_chunk<K>(ra, nbs_addr + 256u, p_addr + 256u, C, u);
+        tmem_wait_ld();
+        tmem_ld32_issue(taddr, ra);
+        bound_chunk<K>(rb, nbs_addr + 384u, p_addr + 384u, C, u);
+        tmem_wait_ld();
+    }
+    tmem_ld32_issue(taddr + 32u, rb);
+    scan_chunk<K, CAP, !TWO_PASS>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, overflow);
+    __syncwarp();
+    tmem_wait_ld();
+    tmem_ld32_issue(taddr + 64u, ra);
+    scan_chunk<K, CAP, !TWO_PASS>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, overflow);
+    __syncwarp();
+    tmem_wait_ld();
+    tmem_ld32_issue(taddr + 96u, rb);
+    scan_chunk<K, CAP, !TWO_PASS>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, overflow);
+    __syncwarp();
+    tmem_wait_ld();
+    scan_chunk<K, CAP, !TWO_PASS>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, overflow);
 }
 
 struct TcParams {
     int64_t n_points;
     int n_mtiles;
-    int nt_ref, nt_pos, nt_neg;          // reference tiles of each class (each class padded to a multiple of 128 rows)
-    const float *nbs;                    // [ (nt_ref + nt_pos + nt_neg) * 128 ] scaled squared norms, PAD_NORM on padding rows
-    int *cand;                           // [n_points, 16] candidate indices within their class, -1 = none
-    float *approx;                       // [n_points, 16] ranking values v = 2^23 (|b|^2 - 2 a.b) of the candidates
+    int nt_ref, nt_pos, nt_neg;          // column tiles of each class (each class padded to a multiple of 128 rows)
+    int n_refs, n_cent_pos, n_cent_neg;  // real columns of each class
+    const float *nbs;                    // [(nt_ref + nt_pos + nt_neg) * 128] 2^23 |b'|^2, PAD_NORM on padding rows
+    const float *pnorm;                  // same layout: P_j = |B~_j| rounded up, 0 on padding rows
+    const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
+    uint2 *cand;                         // [n_points, 16] (lower bound as float bits, column within its class)
+    int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
+    uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | overflow << 24
 };
 
+template <int KN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-score_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcParams p) {
+score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sm_a = smem_base;                                   // [hi chunk 0..3][lo chunk 0..3]
-    const uint32_t sm_b = smem_base + A_BYTES;                         // NSTAGE operand blocks
-    const uint32_t sm_stack = sm_b + NSTAGE * BLOCK_BYTES;             // per epilogue warp: [8 column quads][32 lanes] x 16 bytes
-    const uint32_t sm_x = sm_stack + STACK_BYTES;                      // barriers, tmem pointer, norm staging
+    const uint32_t smem_base = smem_u32(smem_raw);
+    const uint32_t sm_a = smem_base;                                   // [half 0..1][chunk 0..3] blocks of 16 KB
+    const uint32_t sm_b = smem_base + A_BYTES;                         // NSTAGE blocks
+    const uint32_t sm_cand = sm_b + NSTAGE * BLOCK_BYTES;              // [16 entries][256 rows] x 8 bytes
+    const uint32_t sm_stg = sm_cand + CAND_BYTES;                      // [set][nbs | P][128] floats
+    const uint32_t sm_x = sm_stg + STG_BYTES;                          // barriers, tmem pointer
     const uint32_t bar_a_full = sm_x + 0, bar_a_empty = sm_x + 8;
     const uint32_t bar_b_full = sm_x + 16, bar_b_empty = sm_x + 16 + 8 * NSTAGE;
     const uint32_t bar_t_full = sm_x + 16 + 16 * NSTAGE, bar_t_empty = bar_t_full + 16;
-    const uint32_t tmem_slot = bar_t_empty + 16;
-    const uint32_t sm_nbs = sm_x + 512;                                // [NGROUP][128] floats
-    unsigned char *generic_x = smem_raw + (sm_x - smem_u32(smem_raw));
+    const uint32_t bar_n_full = bar_t_empty + 16;                      // nbs / P staging of an accumulator set has landed
+    const uint32_t tmem_slot = bar_n_full + 16;
+    unsigned char *generic_x = smem_raw + (sm_x - smem_base);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nt_total = p.nt_ref + p.nt_pos + p.nt_neg;
 
     if (threadIdx.x == 0) {
+        if (smem_base & 1023u) __trap();                               // SWIZZLE_128B tiles need 1024-byte alignment
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_t_full + 8 * b, 1); mbar_init(bar_t_empty + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_t_full + 8 * b, 1);
+            mbar_init(bar_t_empty + 8 * b, NEPI / 32);
+            mbar_init(bar_n_full + 8 * b, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -227,103 +366,123 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t bstage = 0, bphase = 0;
+            uint32_t bstage = 0, bphase = 0, tile = 0;
             int it = 0;
             for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
                 mbar_wait(bar_a_empty, (uint32_t)((it & 1) ^ 1));
                 mbar_expect_tx(bar_a_full, A_BYTES);
-                for (int kc = 0; kc < NKC; ++kc) {
-                    tma_load_2d(sm_a + kc * BLOCK_BYTES, &map_a_hi, bar_a_full, kc * BK, mt * BM);
-                    tma_load_2d(sm_a + (NKC + kc) * BLOCK_BYTES, &map_a_lo, bar_a_full, kc * BK, mt * BM);
-                }
-                for (int nt = 0; nt < nt_total; ++nt) {
-                    for (int blk = 0; blk < 2 * NKC; ++blk) {           // hi(0), lo(0), hi(1), lo(1), ...
+                for (int h = 0; h < 2; ++h)
+                    for (int kc = 0; kc < NKC; ++kc)
+                        tma_load_2d(sm_a + (h * NKC + kc) * BLOCK_BYTES, &map_a, bar_a_full, kc * BK, mt * MT + h * BM);
+                for (int nt = 0; nt < nt_total; ++nt, ++tile) {
+                    for (int kc = 0; kc < NKC; ++kc) {
                         mbar_wait(bar_b_empty + 8 * bstage, bphase ^ 1u);
                         mbar_expect_tx(bar_b_full + 8 * bstage, BLOCK_BYTES);
-                        tma_load_2d(sm_b + bstage * BLOCK_BYTES, (blk & 1) ? &map_b_lo : &map_b_hi, bar_b_full + 8 * bstage,
-                                    (blk >> 1) * BK, nt * BN);
+                        tma_load_2d(sm_b + bstage * BLOCK_BYTES, &map_b, bar_b_full + 8 * bstage, kc * BK, nt * BN);
                         if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
                     }
+                    // |b|^2 and P of this tile for the epilogue, once the epilogue has let go of the set (two tiles ago)
+                    const uint32_t set = tile & 1u;
+                    mbar_wait(bar_t_empty + 8 * set, ((tile >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(bar_n_full + 8 * set, 2 * BN * 4);
+                    bulk_load(sm_stg + set * (2 * BN * 4), p.nbs + (int64_t)nt * BN, BN * 4, bar_n_full + 8 * set);
+                    bulk_load(sm_stg + set * (2 * BN * 4) + BN * 4, p.pnorm + (int64_t)nt * BN, BN * 4, bar_n_full + 8 * set);
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t bstage = 0, bphase = 0, tile = 0;
-            int it = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
-                mbar_wait(bar_a_full, (uint32_t)(it & 1));
-                for (int nt = 0; nt < nt_total; ++nt, ++tile) {
-                    const uint32_t buf = tile & 1u;
-                    mbar_wait(bar_t_empty + 8 * buf, ((tile >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + buf * BN;
-                    for (int blk = 0; blk < 2 * NKC; ++blk) {
-                        const int kc = blk >> 1;
-                        mbar_wait(bar_b_full + 8 * bstage, bphase);
-                        tc_fence_after();
-                        const uint32_t a_hi = sm_a + kc * BLOCK_BYTES, a_lo = sm_a + (NKC + kc) * BLOCK_BYTES;
-                        const uint32_t b = sm_b + bstage * BLOCK_BYTES;
+        // The whole warp walks the loop so that descriptors and barrier addresses live in uniform registers; one elected
+        // lane issues the tensor-core instructions.  Descriptors differ only in their 14-bit address field (16-byte units).
+        const uint64_t desc_hi = smem_desc(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo = (uint32_t)smem_desc(0);
+        const uint32_t a_lo = desc_lo | ((sm_a & 0x3FFFFu) >> 4), b_lo = desc_lo | ((sm_b & 0x3FFFFu) >> 4);
+        uint32_t bstage = 0, bphase = 0, tile = 0;
+        int it = 0;
+        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+            mbar_wait(bar_a_full, (uint32_t)(it & 1));
+            for (int nt = 0; nt < nt_total; ++nt, ++tile) {
+                const uint32_t set = tile & 1u;
+                mbar_wait(bar_t_empty + 8 * set, ((tile >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + set * (2 * BN);
 #pragma unroll
-                        for (int ks = 0; ks < BK / 16; ++ks) {
-                            const uint32_t o = ks * 32;          // 16 halves = 32 bytes along K inside the swizzle row
-                            if ((blk & 1) == 0) {                // b = hi block: hi.hi and lo.hi
-                                umma_f16(tmem_d, smem_desc(a_hi + o), smem_desc(b + o), (blk | ks) ? 1u : 0u);
-                                umma_f16(tmem_d, smem_desc(a_lo + o), smem_desc(b + o), 1u);
-                            } else {                             // b = lo block: hi.lo
-                                umma_f16(tmem_d, smem_desc(a_hi + o), smem_desc(b + o), 1u);
+                for (int kc = 0; kc < NKC; ++kc) {
+                    mbar_wait(bar_b_full + 8 * bstage, bphase);
+                    tc_fence_after();
+                    const uint32_t b_blk = b_lo + bstage * (BLOCK_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {   // 16 halves = 32 bytes along K inside the swizzle row
+                                const uint32_t a_blk = a_lo + (h * NKC + kc) * (BLOCK_BYTES >> 4) + ks * 2;
+                                umma_f16(tmem_d + h * BN, desc_hi | a_blk, desc_hi | (b_blk + ks * 2), (kc | ks) ? 1u : 0u);
                             }
                         }
                         umma_commit(bar_b_empty + 8 * bstage);    // block reusable once these MMAs have read it
-                        if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
+                        if (kc == NKC - 1) umma_commit(bar_t_full + 8 * set);            // accumulator set complete
                     }
-                    umma_commit(bar_t_full + 8 * buf);            // accumulator complete
+                    __syncwarp();
+                    if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
                 }
-                umma_commit(bar_a_empty);                          // A tile no longer read
             }
+            if (elect_one()) umma_commit(bar_a_empty);            // A tile no longer read
+            __syncwarp();
         }
     } else {
-        // ================= epilogue: 2 groups x 4 warps; thread = contig row = tensor-memory lane =================
+        // ================= epilogue: 8 warps; thread = contig row = tensor-memory lane =================
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
-        const int group = (warp - 2) >> 2;                         // owns reference tiles with (tile & 1) == group
-        const int epi_tid = ((warp - 2) & 3) * 32 + lane;          // 0..127 inside the group
-        const uint32_t stack_addr = sm_stack + (uint32_t)(warp - 2) * 4096u + 16u * lane;
-        const uint32_t nbs_addr = sm_nbs + (uint32_t)group * (BN * 4);
-        for (int mt = blockIdx.x, it = 0; mt < p.n_mtiles; mt += gridDim.x, ++it) {
-            float wr[LREF], wp[LCEN], wn[LCEN];
-            int ir[LREF], ip[LCEN], in_[LCEN];
+        const int half = (warp - 2) >> 2;                          // which 128-row MMA block
+        const int row_in_tile = half * BM + q * 32 + lane;
+        const uint32_t cand_addr = sm_cand + 8u * (uint32_t)row_in_tile;
+        uint32_t tile = 0;
+        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+            const int64_t row = (int64_t)mt * MT + row_in_tile;
+            float C = (row < p.n_points && p.debug != 2) ? p.crow[row] : NAN;
+            const bool live = C >= 0.0f;                           // false for padding rows and NaN feature rows
+            const float init = live ? INFINITY : -INFINITY;        // -inf: nothing ever qualifies
+            if (!live) C = 0.0f;
+            float ur[KN], up[1], un[1];
 #pragma unroll
-            for (int i = 0; i < LREF; ++i) { wr[i] = INFINITY; ir[i] = -1; }
-#pragma unroll
-            for (int i = 0; i < LCEN; ++i) { wp[i] = INFINITY; ip[i] = -1; wn[i] = INFINITY; in_[i] = -1; }
+            for (int i = 0; i < KN; ++i) ur[i] = init;
+            up[0] = init; un[0] = init;
+            int cnt_r = 0, cnt_p = 0, cnt_n = 0;
+            bool overflow = false;
 
-            const uint32_t tile0 = (uint32_t)it * (uint32_t)nt_total;      // running tile index of this CTA
-            for (int nt = 0; nt < nt_total; ++nt) {
-                const uint32_t tile = tile0 + (uint32_t)nt;
-                if ((int)(tile & 1u) != group) continue;
-                const uint32_t buf = tile & 1u;
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");       // previous tile's norm reads are done
-                sts_u32(nbs_addr + 4u * epi_tid, __float_as_uint(p.nbs[(int64_t)nt * BN + epi_tid]));
-                mbar_wait(bar_t_full + 8 * buf, (tile >> 1) & 1u);
+            for (int nt = 0; nt < nt_total; ++nt, ++tile) {
+                const uint32_t set = tile & 1u;
+                const uint32_t stg = sm_stg + set * (2 * BN * 4);
+                mbar_wait(bar_n_full + 8 * set, (tile >> 1) & 1u);
+                mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
                 tc_fence_after();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");       // norm staging visible to the group
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-                if (nt < p.nt_ref) scan_tile<LREF>(taddr, nbs_addr, stack_addr, nt * BN, wr, ir);
-                else if (nt < p.nt_ref + p.nt_pos) scan_tile<LCEN>(taddr, nbs_addr, stack_addr, (nt - p.nt_ref) * BN, wp, ip);
-                else scan_tile<LCEN>(taddr, nbs_addr, stack_addr, (nt - p.nt_ref - p.nt_pos) * BN, wn, in_);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
+                if (p.debug == 1) {
+                } else if (nt == 0)
+                    scan_tile<KN, CAP_R, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, overflow);
+                else if (nt < p.nt_ref)
+                    scan_tile<KN, CAP_R, false>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, overflow);
+                else if (nt == p.nt_ref)
+                    scan_tile<1, CAP_C, true>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, overflow);
+                else if (nt < p.nt_ref + p.nt_pos)
+                    scan_tile<1, CAP_C, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, overflow);
+                else if (nt == p.nt_ref + p.nt_pos)
+                    scan_tile<1, CAP_C, true>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, overflow);
+                else
+                    scan_tile<1, CAP_C, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, overflow);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_t_empty + 8 * buf);
+                if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
             }
-            const int64_t row = (int64_t)mt * BM + q * 32 + lane;
+            // drop what the final thresholds exclude, then publish the row's candidates
+            cand_prune<CAP_R>(cand_addr, 0, cnt_r, ur[KN - 1]);
+            cand_prune<CAP_C>(cand_addr, CAP_R, cnt_p, up[0]);
+            cand_prune<CAP_C>(cand_addr, CAP_R + CAP_C, cnt_n, un[0]);
             if (row < p.n_points) {
-                int *c = p.cand + row * NCAND + group * NSLOT;
-                float *a = p.approx + row * NCAND + group * NSLOT;
+                uint2 *out = p.cand + row * NENT;
 #pragma unroll
-                for (int i = 0; i < LREF; ++i) { c[i] = ir[i]; a[i] = wr[i]; }
-#pragma unroll
-                for (int i = 0; i < LCEN; ++i) { c[LREF + i] = ip[i]; a[LREF + i] = wp[i]; c[LREF + LCEN + i] = in_[i]; a[LREF + LCEN + i] = wn[i]; }
+                for (int e = 0; e < NENT; ++e) out[e] = lds_v2(cand_addr + (uint32_t)e * (NEPI * 8));
+                p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (overflow ? (1u << 24) : 0u);
             }
         }
     }
@@ -335,82 +494,98 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
 }
 
-// ---------------- operand preparation: float64 rows -> centred, 2^12-scaled FP16 hi / lo ----------------
-// Distances are translation invariant, so every row is shifted by the uniform vector 1/256 before the split: frequency
-// rows sum to 1, which makes |x - u|^2 = |x|^2 - 1/256 about 4.5x smaller than |x|^2 and shrinks the absolute error of the
-// FP32-accumulated ranking value by the same factor.  (Exact distances are always formed from the unshifted float64 rows.)
-__device__ __forceinline__ void split_store(double x, __half *hi, __half *lo, int64_t o) {
-    const double s = x * (double)SCALE;
-    const __half h = __float2half_rn((float)s);
-    const __half l = __float2half_rn((float)(s - (double)__half2float(h)));
-    hi[o] = h;
-    lo[o] = l;
-}
-
-// rows [0, n_src) from src, rows [n_src, n_rows) zero padding; squared norms of the raw rows (float64, for the exact
-// kernel), of the centred rows (float64, for the error bound) and of the centred rows scaled to ranking units (FP32)
+// ---------------- operand preparation: float64 rows -> centred, 2^12-scaled FP16 + exact residual norms ----------------
+// Distances are translation invariant, so every row is shifted by the uniform vector 1/256 before rounding: frequency rows
+// sum to 1, which makes |x - u|^2 = |x|^2 - 1/256 about 4.5x smaller than |x|^2 and shrinks every error term with it.
+// (Exact distances are always formed from the unshifted float64 rows.)
 //
 // Reference rows are laid out in a scrambled order, destination row r <- source row (perm_a * r + perm_c) mod n_src with
 // perm_a ~ 0.618 n_src coprime to n_src.  The shipped tables are sorted by taxonomy, so distances to a contig run in long
-// monotone stretches along the file and the running-shortlist threshold of the epilogue would be beaten far more often
-// than the 8/j of an exchangeable order; a golden-ratio stride makes every prefix an even sample of the whole file.
-__global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a,
-                                    int64_t perm_c, __half *__restrict__ hi, __half *__restrict__ lo,
-                                    double *__restrict__ norm64, double *__restrict__ cnorm64, float *__restrict__ nbs) {
+// monotone stretches along the file and the running threshold of the epilogue would be beaten far more often than in an
+// exchangeable order; a golden-ratio stride makes every prefix an even sample of the whole file.
+struct PrepConsts {            // device-resident, written by the reference pass, read by the query pass
+    float rho;                 // max_j (dB_j + eps_acc (P_j + dB_j)) / P_j
+    float pmax;                // max_j P_j
+};
+
+__device__ __forceinline__ float float_up(double x) {           // a float that is >= x (x >= 0)
+    float f = (float)x;
+    return ((double)f >= x) ? f : __uint_as_float(__float_as_uint(f) + 1u);
+}
+
+// is_ref = 1: reference / centroid rows: FP16 operand, nbs, P, norms, and rho / pmax by atomic max (positive floats order as ints)
+// is_ref = 0: query rows: FP16 operand, norms and C_row (reads rho / pmax, so it must run after every is_ref pass)
+__global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
+                                    int is_ref, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
+                                    float *__restrict__ nbs, float *__restrict__ pnorm, float *__restrict__ crow,
+                                    PrepConsts *consts) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double shift = 1.0 / (double)KDIM;
+    float rho = 0.f, pmax = 0.f;
+    if (!is_ref) { rho = consts->rho; pmax = consts->pmax; }
     for (int64_t r = warp; r < n_rows; r += n_warps) {
-        double s = 0.0, sc = 0.0;
+        double s = 0.0, sc = 0.0, sd = 0.0, sh = 0.0;       // |x|^2, |x - u|^2, |B~ - B|^2, |B|^2 (scaled units)
         const int64_t sr = (r < n_src) ? (perm_a * r + perm_c) % n_src : 0;
         for (int d = lane; d < KDIM; d += 32) {
             const double x = (r < n_src) ? src[sr * KDIM + d] : shift;
             const double xc = x - shift;
-            split_store(xc, hi, lo, r * KDIM + d);
+            const double t = xc * (double)SCALE;
+            const __half h = __float2half_rn((float)t);
+            const double hv = (double)__half2float(h);
+            op[r * KDIM + d] = h;
             s = fma(x, x, s);
             sc = fma(xc, xc, sc);
+            sd = fma(t - hv, t - hv, sd);
+            sh = fma(hv, hv, sh);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s += __shfl_xor_sync(FULL, s, o);
             sc += __shfl_xor_sync(FULL, sc, o);
+            sd += __shfl_xor_sync(FULL, sd, o);
+            sh += __shfl_xor_sync(FULL, sh, o);
         }
         if (lane == 0) {
-            if (norm64 && r < n_src) norm64[sr] = s;
-            if (cnorm64 && r < n_src) cnorm64[sr] = sc;
-            if (nbs) nbs[r] = (r < n_src) ? (float)(sc * (double)NORM_SCALE) : PAD_NORM;
+            const bool real = r < n_src;
+            if (norm64 && real) norm64[sr] = s;
+            if (cnorm64 && real) cnorm64[sr] = sc;
+            const double P = sqrt(sc) * (double)SCALE * (1.0 + 1e-12);     // |B~| (or |A~|), a hair up against the sqrt rounding
+            const double dB = sqrt(sd) * (1.0 + 1e-12);
+            const double nH = sqrt(sh) * (1.0 + 1e-12);
+            if (is_ref) {
+                nbs[r] = real ? (float)(sc * NORM_SCALE) : PAD_NORM;
+                pnorm[r] = real ? float_up(P) : 0.0f;
+                if (real && P > 0.0) {
+                    atomicMax(reinterpret_cast<int *>(&consts->rho), __float_as_int(float_up((dB + EPS_ACC * (P + dB)) / P)));
+                    atomicMax(reinterpret_cast<int *>(&consts->pmax), __float_as_int(float_up(P)));
+                }
+            } else if (real) {
+                // err_j <= dA P_j + nA dB_j + eps_acc nA |B_j| + (FP32 roundings of nbs_j, of nbs_j - acc_j and of the fma)
+                //       <= P_j (dA + nA rho + 2^-21 (pmax + nA))        then 1 % on top for the FP32 arithmetic on the bounds
+                const double c = (dB + nH * (double)rho + (double)(pmax + float_up(nH)) / 2097152.0) * 1.01;
+                crow[sr] = isnan(sc) ? NAN : float_up(c);
+            }
         }
     }
 }
 
-// ---------------- decision + exact re-measurement of the shortlists ----------------
-// The ranking value v_j = 2^23 (|b_j|^2 - 2 a.b_j) (centred rows) of reference j differs from the exact
-// 2^23 (d2_j - |a|^2) by at most Ev = 2^23 * RANK_EPS * (|a|^2 + |b_j|^2): tcgen05 accumulates 48 MMAs per value in FP32 with
-// truncation (<= 48 * 2^-23 = 2^-17.4 relative to the sum of the magnitudes), the split drops 2^-22; measured maximum on
-// 1.3e6 (contig, reference) pairs: 2^-17.3.  RANK_EPS = 2^-15 leaves a factor 5.  For any reference that could still matter
-// |b|^2 <= 2 |a|^2 + 2 d2, so one bound per row is used: E = RANK_EPS * (3 |a|^2 + 2 d2_last).
-//
-// k nearest neighbours: every reference outside the band {v <= v_k + 2 Ev} is provably farther than the k-th nearest.
-// If the band reaches the end of the shortlist, unseen references may belong to it: the row goes to the exhaustive kernel.
-// Otherwise the vote is read off the band when it has exactly k members or a single label; only a mixed band is
-// re-measured exactly (float64, direct difference).  Centroids: the band around the best ranking value is re-measured
-// exactly and the nearest taken; its exact distance enters the score.
-constexpr double RANK_EPS = 1.0 / 32768.0;      // 2^-15
-
-struct RerankParams {
+// ---------------- decision: candidates -> vote / centroid distances, exact float64 where it matters ----------------
+struct DecideParams {
     const double *points; int64_t n_points;
     const double *refs; int64_t n_refs; int64_t n_positive;
     int64_t perm_a, perm_c;            // reference candidate index -> original row: (perm_a * idx + perm_c) mod n_refs
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
-    const double *cnorm_points;        // centred squared norms of the query rows
-    const double *cnorm_refs;
-    const int *cand; const float *approx;
+    int64_t ref_pad, cp_pad;           // offsets of the centroid classes in the padded column layout (pnorm)
+    const double *cnorm_points;        // centred squared norms of the query rows (NaN = NaN feature row)
+    const float *crow; const float *pnorm;
+    const uint2 *cand; const uint32_t *meta;
     int k_neighbors;
     double *knn, *kmeans, *combo;
     int64_t *fallback_rows; unsigned long long *fallback_count;
-    float *max_rank_error;             // when non-null: re-measure every reference candidate and record the ranking error
+    float *stats;                      // when non-null: [0] max |x - exact| / (C P) (must stay <= 1), [1] max |x - exact| in d2 units
     unsigned long long *rows_remeasured;
 };
 
@@ -426,80 +601,73 @@ __device__ __forceinline__ double warp_exact_d2(const double (&x)[KDIM / 32], co
     return acc;
 }
 
-__device__ __forceinline__ float warp_min_f(float v) {
+__device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
 
-// One warp per contig; lane l holds candidate l: epilogue group l / 16, slot l % 16 (0..7 references, 8..11 positive
-// centroids, 12..15 negative centroids).  Each group lists the best candidates among ITS reference tiles, so the union of
-// the two lists contains the global best and every unlisted reference of group g ranks behind slot 7 of group g.
-__global__ void __launch_bounds__(256) rerank_kernel(RerankParams p) {
+// One warp per contig; lane l < 16 holds candidate slot l (0..9 references, 10..12 positive centroids, 13..15 negative).
+__global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double to_d2 = 1.0 / (double)NORM_SCALE;
     const int kn = p.k_neighbors;
-    const int slot = lane & (NSLOT - 1);
-    const bool ref_lane = slot < LREF;
     for (int64_t row = warp; row < p.n_points; row += n_warps) {
-        const double *pt = p.points + row * KDIM;
-        double x[KDIM / 32];
-#pragma unroll
-        for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
         const double na = p.cnorm_points[row];
-        int my_cand = p.cand[row * NCAND + lane];
-        const float my_v = (my_cand >= 0) ? p.approx[row * NCAND + lane] : INFINITY;
-        if (ref_lane && my_cand >= 0) my_cand = (int)((p.perm_a * my_cand + p.perm_c) % p.n_refs);   // back to file order
         bool fallback = false;
         double knn = NAN, km = NAN;
-
         if (!isnan(na)) {
+            const double *pt = p.points + row * KDIM;
+            double x[KDIM / 32];
+#pragma unroll
+            for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
+            const uint32_t meta = p.meta[row];
+            const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
+            fallback = (meta >> 24) != 0u || cnt_r < kn;
+            const double C = (double)p.crow[row];
+            uint2 ent = make_uint2(0u, 0u);
+            if (lane < NENT) ent = p.cand[row * NENT + lane];
+            const bool is_ref = lane < CAP_R && lane < cnt_r;
+            const bool is_pos = lane >= CAP_R && lane < CAP_R + cnt_p && lane < CAP_R + CAP_C;
+            const bool is_neg = lane >= CAP_R + CAP_C && lane < CAP_R + CAP_C + cnt_n && lane < NENT;
+            const int col = (int)ent.y;
+            int64_t pcol = col;                                        // column in the padded layout of pnorm
+            if (is_pos) pcol += p.ref_pad;
+            if (is_neg) pcol += p.ref_pad + p.cp_pad;
+            const bool valid = is_ref || is_pos || is_neg;
+            const double width = valid ? 2.0 * C * (double)p.pnorm[pcol] : 0.0;
+            const double lower = valid ? (double)__uint_as_float(ent.x) : INFINITY;
+            const double upper = valid ? lower + width : INFINITY;
+            int my_idx = col;                                          // index in the caller's arrays
+            if (is_ref) my_idx = (int)((p.perm_a * (int64_t)col + p.perm_c) % p.n_refs);
+
             // ---------------- k nearest references ----------------
-            {
-                const bool valid = ref_lane && my_cand >= 0;
-                // every unlisted reference ranks at or behind the last slot of its own group's (full) list
-                const float v_lim = fminf(__shfl_sync(FULL, my_v, LREF - 1), __shfl_sync(FULL, my_v, NSLOT + LREF - 1));
-                const float v_max = warp_max_f(valid ? my_v : -INFINITY);
-                const double d_bound = fmax(na + (double)(isinf(v_lim) ? v_max : v_lim) * to_d2, 0.0);
-                const float ev2 = (float)(2.0 * RANK_EPS * (3.0 * na + 2.0 * d_bound) * (double)NORM_SCALE);
-                int rank = 0;                                         // position of my candidate in the merged order
+            if (!fallback) {
+                int rank = 0;                                          // position of my upper bound among the candidates'
 #pragma unroll
-                for (int g = 0; g < NGROUP; ++g)
-#pragma unroll
-                    for (int sl = 0; sl < LREF; ++sl) {
-                        const int src = g * NSLOT + sl;
-                        const float ov = __shfl_sync(FULL, my_v, src);
-                        const int oi = __shfl_sync(FULL, my_cand, src);
-                        if (oi >= 0 && src != lane && (ov < my_v || (ov == my_v && oi < my_cand))) ++rank;
-                    }
-                const unsigned kth = __ballot_sync(FULL, valid && rank == kn - 1);     // exists: k_neighbors <= n_refs
-                const float v_k = __shfl_sync(FULL, my_v, __ffs(kth) - 1);
-                const bool in_band = valid && my_v <= v_k + ev2;
+                for (int s = 0; s < CAP_R; ++s) {
+                    const double ou = __shfl_sync(FULL, upper, s);
+                    if (s < cnt_r && s != lane && (ou < upper || (ou == upper && s < lane))) ++rank;
+                }
+                const unsigned kth = __ballot_sync(FULL, is_ref && rank == kn - 1);
+                const double u_k = __shfl_sync(FULL, upper, __ffs(kth) - 1);
+                const bool in_band = is_ref && lower <= u_k;
                 const unsigned band = __ballot_sync(FULL, in_band);
-                const unsigned pos_mask = __ballot_sync(FULL, in_band && my_cand < p.n_positive);
-                const bool complete = isinf(v_lim) || (v_lim > v_k + ev2);
+                const unsigned pos_mask = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
                 const int n_band = __popc(band);
-                if (!complete || kth == 0u) {
-                    fallback = true;
-                } else if (n_band == kn || pos_mask == 0u || pos_mask == band) {
+                if (n_band == kn || pos_mask == 0u || pos_mask == band) {
                     // the k nearest are exactly the band, or every possible member votes the same way
                     const int pos = (pos_mask == band) ? kn : ((pos_mask == 0u) ? 0 : __popc(pos_mask));
                     knn = (2 * pos > kn) ? 1.0 : -1.0;               // 2 * (predict - 0.5), scripts/learning.py:128
                 } else {
-                    // mixed band: exact distances of its members, k smallest (ties: lower reference index first)
+                    // undecided: exact distances of the band, k smallest (ties: lower reference index first)
                     double my_d2 = INFINITY;
                     unsigned rest = band;
                     while (rest) {
                         const int s = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const int idx = __shfl_sync(FULL, my_cand, s);
+                        const int idx = __shfl_sync(FULL, my_idx, s);
                         const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
                         if (lane == s) my_d2 = d;
                     }
@@ -509,29 +677,30 @@ __global__ void __launch_bounds__(256) rerank_kernel(RerankParams p) {
                         const int s = __ffs(rest) - 1;
                         rest &= rest - 1;
                         const double od = __shfl_sync(FULL, my_d2, s);
-                        const int oi = __shfl_sync(FULL, my_cand, s);
-                        if (s != lane && (od < my_d2 || (od == my_d2 && oi < my_cand))) ++erank;
+                        const int oi = __shfl_sync(FULL, my_idx, s);
+                        if (s != lane && (od < my_d2 || (od == my_d2 && oi < my_idx))) ++erank;
                     }
                     const unsigned top = __ballot_sync(FULL, in_band && erank < kn);
                     const int pos = __popc(top & pos_mask);
                     knn = (2 * pos > kn) ? 1.0 : -1.0;
                     if (p.rows_remeasured && lane == 0) atomicAdd(p.rows_remeasured, 1ull);
                 }
-                if (p.max_rank_error) {           // diagnostics: ranking error of every reference candidate
-                    float worst = 0.f, worst_rel = 0.f;
-                    for (int s = 0; s < NCAND; ++s) {
-                        const int idx = __shfl_sync(FULL, my_cand, s);
-                        const float vs = __shfl_sync(FULL, my_v, s);
-                        if (idx < 0 || (s & (NSLOT - 1)) >= LREF) continue;
-                        const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
-                        const double err = fabs(na + (double)vs * to_d2 - d);
-                        worst = fmaxf(worst, (float)err);
-                        worst_rel = fmaxf(worst_rel, (float)(err / (na + p.cnorm_refs[idx])));
-                    }
-                    if (lane == 0) {
-                        atomicMax(reinterpret_cast<int *>(p.max_rank_error), __float_as_int(worst));
-                        atomicMax(reinterpret_cast<int *>(p.max_rank_error + 1), __float_as_int(worst_rel));
-                    }
+            }
+            if (p.stats) {                    // diagnostics: how much of the proven interval the true value uses
+                float worst_use = 0.f, worst_abs = 0.f;
+                for (int s = 0; s < CAP_R; ++s) {
+                    if (s >= cnt_r) break;
+                    const int idx = __shfl_sync(FULL, my_idx, s);
+                    const double lo_s = __shfl_sync(FULL, lower, s), w_s = __shfl_sync(FULL, width, s);
+                    const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
+                    const double exact = (d - na) * NORM_SCALE;                 // what the ranking value estimates
+                    const double err = fabs(lo_s + 0.5 * w_s - exact);
+                    worst_abs = fmaxf(worst_abs, (float)(err / NORM_SCALE));
+                    if (w_s > 0.0) worst_use = fmaxf(worst_use, (float)(err / (0.5 * w_s)));
+                }
+                if (lane == 0) {
+                    atomicMax(reinterpret_cast<int *>(p.stats), __float_as_int(worst_use));
+                    atomicMax(reinterpret_cast<int *>(p.stats + 1), __float_as_int(worst_abs));
                 }
             }
             // ---------------- nearest centroid of each class ----------------
@@ -539,21 +708,16 @@ __global__ void __launch_bounds__(256) rerank_kernel(RerankParams p) {
                 double e2[2];
 #pragma unroll
                 for (int cls = 0; cls < 2; ++cls) {
-                    const int base = LREF + cls * LCEN;
-                    const bool mine = slot >= base && slot < base + LCEN && my_cand >= 0;
-                    const float v_0 = warp_min_f(mine ? my_v : INFINITY);
-                    const float v_lim = fminf(__shfl_sync(FULL, my_v, base + LCEN - 1), __shfl_sync(FULL, my_v, NSLOT + base + LCEN - 1));
-                    const float v_max = warp_max_f(mine ? my_v : -INFINITY);
-                    const double d_bound = fmax(na + (double)(isinf(v_lim) ? v_max : v_lim) * to_d2, 0.0);
-                    const float ev2 = (float)(2.0 * RANK_EPS * (3.0 * na + 2.0 * d_bound) * (double)NORM_SCALE);
+                    const bool mine = cls ? is_neg : is_pos;
+                    if ((cls ? cnt_n : cnt_p) < 1) fallback = true;
+                    const double u_1 = warp_min_d(mine ? upper : INFINITY);
                     const double *cents = cls ? p.cent_neg : p.cent_pos;
-                    unsigned rest = __ballot_sync(FULL, mine && my_v <= v_0 + ev2);
-                    if (!(isinf(v_lim) || v_lim > v_0 + ev2)) fallback = true;
+                    unsigned rest = __ballot_sync(FULL, mine && lower <= u_1);
                     double best = INFINITY;
                     while (rest) {
                         const int s = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const int idx = __shfl_sync(FULL, my_cand, s);
+                        const int idx = __shfl_sync(FULL, my_idx, s);
                         best = fmin(best, warp_exact_d2(x, cents + (int64_t)idx * KDIM, lane));
                     }
                     e2[cls] = best;
@@ -571,6 +735,87 @@ __global__ void __launch_bounds__(256) rerank_kernel(RerankParams p) {
                 if (p.kmeans) p.kmeans[row] = km;
                 if (p.combo) p.combo[row] = knn + km;                   // scripts/phamer.py:313
             }
+        }
+    }
+}
+
+// ---------------- rows the decision kernel could not settle: exhaustive float64, one CTA per row ----------------
+// Direct-difference float64 distance to EVERY reference and centroid (the same arithmetic score_decide_kernel uses for its
+// candidates), 8 warps striding over the columns, k smallest by (distance, index).  The rows are few (candidate-buffer
+// overflow: contigs sitting inside a dense cloud of near-identical references), so the grid is small and persistent and
+// reads the row count on the device.
+constexpr int FB_K = 5;
+struct FallbackParams {
+    const double *points;
+    const double *refs; int64_t n_refs; int64_t n_positive;
+    const double *cent_pos; int64_t n_cent_pos;
+    const double *cent_neg; int64_t n_cent_neg;
+    const int64_t *rows; const unsigned long long *count;
+    int k_neighbors;
+    double *knn, *kmeans, *combo;
+};
+
+__global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
+    __shared__ double s_d[8][FB_K];
+    __shared__ int s_i[8][FB_K];
+    __shared__ double s_c[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kn = f.k_neighbors;
+    const unsigned long long count = *f.count;
+    for (unsigned long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const int64_t row = f.rows[it];
+        const double *pt = f.points + row * KDIM;
+        double x[KDIM / 32];
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
+        double bd[FB_K];
+        int bi[FB_K];
+#pragma unroll
+        for (int i = 0; i < FB_K; ++i) { bd[i] = INFINITY; bi[i] = -1; }
+        for (int64_t c = warp; c < f.n_refs; c += 8) {          // ascending index per warp: strict '<' keeps the earlier of a tie
+            const double d = warp_exact_d2(x, f.refs + c * KDIM, lane);
+#pragma unroll
+            for (int i = FB_K - 1; i > 0; --i) {
+                const bool shift = d < bd[i - 1], here = d < bd[i];
+                bi[i] = shift ? bi[i - 1] : (here ? (int)c : bi[i]);
+                bd[i] = shift ? bd[i - 1] : (here ? d : bd[i]);
+            }
+            if (d < bd[0]) { bd[0] = d; bi[0] = (int)c; }
+        }
+        double cp = INFINITY, cn = INFINITY;
+        for (int64_t c = warp; c < f.n_cent_pos; c += 8) cp = fmin(cp, warp_exact_d2(x, f.cent_pos + c * KDIM, lane));
+        for (int64_t c = warp; c < f.n_cent_neg; c += 8) cn = fmin(cn, warp_exact_d2(x, f.cent_neg + c * KDIM, lane));
+        __syncthreads();                                        // previous row's merge has finished reading
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < FB_K; ++i) { s_d[warp][i] = bd[i]; s_i[warp][i] = bi[i]; }
+            s_c[warp][0] = cp; s_c[warp][1] = cn;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int pos = 0, head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int t = 0; t < kn; ++t) {                      // k-way merge of the 8 sorted lists by (distance, index)
+                int best = -1;
+                for (int w = 0; w < 8; ++w) {
+                    if (head[w] >= FB_K || s_i[w][head[w]] < 0) continue;
+                    if (best < 0 || s_d[w][head[w]] < s_d[best][head[best]] ||
+                        (s_d[w][head[w]] == s_d[best][head[best]] && s_i[w][head[w]] < s_i[best][head[best]])) best = w;
+                }
+                if (best < 0) break;
+                pos += s_i[best][head[best]] < f.n_positive;
+                ++head[best];
+            }
+            const double knn = (2 * pos > kn) ? 1.0 : -1.0;     // scripts/learning.py:128
+            double km = NAN;
+            if (f.n_cent_pos > 0 && f.n_cent_neg > 0) {
+                double e_pos = INFINITY, e_neg = INFINITY;
+                for (int w = 0; w < 8; ++w) { e_pos = fmin(e_pos, s_c[w][0]); e_neg = fmin(e_neg, s_c[w][1]); }
+                e_pos = sqrt(e_pos); e_neg = sqrt(e_neg);
+                km = tanh((e_neg - e_pos) / (e_pos + e_neg));  // scripts/phamer.py:206-209
+            }
+            if (f.knn) f.knn[row] = knn;
+            if (f.kmeans) f.kmeans[row] = km;
+            if (f.combo) f.combo[row] = knn + km;
         }
     }
 }
@@ -609,13 +854,13 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct TcWorkspace {
-    __half *a_hi, *a_lo, *b_hi, *b_lo;
-    float *nbs;
-    int *cand; float *approx;
+    unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 256-byte header
+    __half *a_op, *b_op;
+    float *nbs, *pnorm, *crow;
+    uint2 *cand; uint32_t *meta;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
-    double *cnorm_points, *cnorm_refs;
-    int64_t *fallback_rows; unsigned long long *fallback_count; float *max_rank_error;
-    unsigned long long *rows_remeasured;
+    double *cnorm_points;
+    int64_t *fallback_rows;
     size_t bytes;
 };
 
@@ -624,22 +869,23 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     size_t off = 0;
     unsigned char *base = static_cast<unsigned char *>(ws);
     auto take = [&](size_t bytes) { unsigned char *p = base ? base + off : nullptr; off += align256(bytes); return p; };
-    w.fallback_count = reinterpret_cast<unsigned long long *>(take(256));
-    w.max_rank_error = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(w.fallback_count) + 64);
-    w.rows_remeasured = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(w.fallback_count) + 128);
-    w.a_hi = reinterpret_cast<__half *>(take((size_t)n * KDIM * 2));
-    w.a_lo = reinterpret_cast<__half *>(take((size_t)n * KDIM * 2));
-    w.b_hi = reinterpret_cast<__half *>(take((size_t)r_pad * KDIM * 2));
-    w.b_lo = reinterpret_cast<__half *>(take((size_t)r_pad * KDIM * 2));
+    unsigned char *head = take(256);
+    w.fallback_count = reinterpret_cast<unsigned long long *>(head);
+    w.stats = reinterpret_cast<float *>(head + 64);
+    w.rows_remeasured = reinterpret_cast<unsigned long long *>(head + 128);
+    w.consts = reinterpret_cast<PrepConsts *>(head + 192);
+    w.a_op = reinterpret_cast<__half *>(take((size_t)n * KDIM * 2));
+    w.b_op = reinterpret_cast<__half *>(take((size_t)r_pad * KDIM * 2));
     w.nbs = reinterpret_cast<float *>(take((size_t)r_pad * 4));
-    w.cand = reinterpret_cast<int *>(take((size_t)n * NCAND * 4));
-    w.approx = reinterpret_cast<float *>(take((size_t)n * NCAND * 4));
+    w.pnorm = reinterpret_cast<float *>(take((size_t)r_pad * 4));
+    w.crow = reinterpret_cast<float *>(take((size_t)n * 4));
+    w.cand = reinterpret_cast<uint2 *>(take((size_t)n * NENT * 8));
+    w.meta = reinterpret_cast<uint32_t *>(take((size_t)n * 4));
     w.norm_points = reinterpret_cast<double *>(take((size_t)n * 8));
     w.norm_refs = reinterpret_cast<double *>(take((size_t)n_refs * 8));
     w.norm_cpos = reinterpret_cast<double *>(take((size_t)n_cp * 8));
     w.norm_cneg = reinterpret_cast<double *>(take((size_t)n_cn * 8));
     w.cnorm_points = reinterpret_cast<double *>(take((size_t)n * 8));
-    w.cnorm_refs = reinterpret_cast<double *>(take((size_t)n_refs * 8));
     w.fallback_rows = reinterpret_cast<int64_t *>(take((size_t)n * 8));
     w.bytes = off;
     return w;
@@ -650,16 +896,28 @@ size_t score_tc_workspace_bytes(int64_t n, int64_t n_refs, int64_t n_cp, int64_t
     return carve_tc(nullptr, n, r_pad, n_refs, n_cp, n_cn).bytes;
 }
 
-bool score_tc_supported(int dim, int k_neighbors, int64_t n_cp, int64_t n_cn) {
-    return dim == KDIM && k_neighbors <= 5 && n_cp > 0 && n_cn > 0;
+bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cp, int64_t n_cn) {
+    return dim == KDIM && (k_neighbors == 1 || k_neighbors == 3 || k_neighbors == 5) && n_refs >= k_neighbors && n_cp > 0 && n_cn > 0;
 }
 
-static int launch_prep(const double *src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, __half *hi, __half *lo,
-                       double *norm64, double *cnorm64, float *nbs, cudaStream_t st) {
+static int launch_prep(const double *src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, __half *op,
+                       double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st) {
     if (n_rows == 0) return PHM_OK;
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, hi, lo, norm64, cnorm64, nbs);
+    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, is_ref, op, norm64, cnorm64, nbs, pnorm,
+                                                          crow, consts);
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}
+
+template <int KN>
+static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const TcParams &p, cudaStream_t st) {
+    auto kern = score_tc_kernel<KN>;
+    PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int grid = sm_count();
+    if (grid > p.n_mtiles) grid = p.n_mtiles;
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
     PHM_CUDA_CHECK(cudaGetLastError());
     return PHM_OK;
 }
@@ -670,76 +928,85 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     const int64_t r_pad = ref_pad + cp_pad + cn_pad;
     TcWorkspace w = carve_tc(ws, n, r_pad, a.n_refs, a.n_cent_pos, a.n_cent_neg);
     if (ws_bytes < w.bytes) { set_error("workspace too small: %zu < %zu", ws_bytes, w.bytes); return PHM_E_WORKSPACE; }
-    PHM_REQUIRE(n < ((int64_t)1 << 31) * BM / 2 && r_pad < ((int64_t)1 << 31), "problem too large for 32-bit TMA coordinates");
+    PHM_REQUIRE(n < ((int64_t)1 << 31) - MT && r_pad < ((int64_t)1 << 31), "problem too large for 32-bit TMA coordinates");
 
     PHM_CUDA_CHECK(cudaMemsetAsync(w.fallback_count, 0, 256, st));
     int rc;
-    // operands
     // golden-ratio stride coprime to n_refs (see tc_prep_rows_kernel)
     int64_t perm_a = (int64_t)(0.6180339887498949 * (double)a.n_refs);
     if (perm_a < 1) perm_a = 1;
     auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
     while (gcd(perm_a, a.n_refs) != 1) ++perm_a;
     const int64_t perm_c = a.n_refs / 3;
-    if ((rc = launch_prep(a.points, n, n, 1, 0, w.a_hi, w.a_lo, w.norm_points, w.cnorm_points, nullptr, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.refs, a.n_refs, ref_pad, perm_a, perm_c, w.b_hi, w.b_lo, w.norm_refs, w.cnorm_refs, w.nbs, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_pos, a.n_cent_pos, cp_pad, 1, 0, w.b_hi + ref_pad * KDIM, w.b_lo + ref_pad * KDIM, w.norm_cpos,
-                          nullptr, w.nbs + ref_pad, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_neg, a.n_cent_neg, cn_pad, 1, 0, w.b_hi + (ref_pad + cp_pad) * KDIM, w.b_lo + (ref_pad + cp_pad) * KDIM,
-                          w.norm_cneg, nullptr, w.nbs + ref_pad + cp_pad, st)) != PHM_OK) return rc;
+    // references and centroids first (they publish rho and pmax), then the queries
+    if ((rc = launch_prep(a.refs, a.n_refs, ref_pad, perm_a, perm_c, 1, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.cent_pos, a.n_cent_pos, cp_pad, 1, 0, 1, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
+                          w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.cent_neg, a.n_cent_neg, cn_pad, 1, 0, 1, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
+                          w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.points, n, n, 1, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
 
-    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
-    if ((rc = make_map(&map_a_hi, w.a_hi, n)) != PHM_OK) return rc;
-    if ((rc = make_map(&map_a_lo, w.a_lo, n)) != PHM_OK) return rc;
-    if ((rc = make_map(&map_b_hi, w.b_hi, r_pad)) != PHM_OK) return rc;
-    if ((rc = make_map(&map_b_lo, w.b_lo, r_pad)) != PHM_OK) return rc;
+    CUtensorMap map_a, map_b;
+    if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;
+    if ((rc = make_map(&map_b, w.b_op, r_pad)) != PHM_OK) return rc;
 
     TcParams p;
     p.n_points = n;
-    p.n_mtiles = (int)((n + BM - 1) / BM);
+    p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
-    p.nbs = w.nbs; p.cand = w.cand; p.approx = w.approx;
-    PHM_CUDA_CHECK(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    int grid = sm_count();
-    if (grid > p.n_mtiles) grid = p.n_mtiles;
-    score_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, p);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
+    p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.meta = w.meta;
+    p.debug = score_debug;
+    switch (a.k_neighbors) {
+        case 1: rc = launch_tc<1>(map_a, map_b, p, st); break;
+        case 3: rc = launch_tc<3>(map_a, map_b, p, st); break;
+        case 5: rc = launch_tc<5>(map_a, map_b, p, st); break;
+        default: set_error("tensor-core scoring supports k_neighbors 1, 3, 5"); return PHM_E_UNSUPPORTED;
+    }
+    if (rc != PHM_OK) return rc;
 
-    RerankParams r;
+    DecideParams r;
     r.points = a.points; r.n_points = n;
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
-    r.cnorm_points = w.cnorm_points; r.cnorm_refs = w.cnorm_refs; r.cand = w.cand; r.approx = w.approx;
+    r.ref_pad = ref_pad; r.cp_pad = cp_pad;
+    r.cnorm_points = w.cnorm_points; r.crow = w.crow; r.pnorm = w.pnorm; r.cand = w.cand; r.meta = w.meta;
     r.k_neighbors = a.k_neighbors;
     r.knn = a.knn; r.kmeans = a.kmeans; r.combo = a.combo;
     r.fallback_rows = w.fallback_rows; r.fallback_count = w.fallback_count;
-    r.max_rank_error = score_collect_stats ? w.max_rank_error : nullptr;
+    r.stats = score_collect_stats ? w.stats : nullptr;
     r.rows_remeasured = w.rows_remeasured;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    rerank_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
+    score_decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
     PHM_CUDA_CHECK(cudaGetLastError());
 
-    // rows whose shortlist could not be proven complete: exhaustive float64 kernel, count read on the device
-    ScoreArgs f = a;
-    f.norm_points = w.norm_points; f.norm_refs = w.norm_refs; f.norm_cpos = w.norm_cpos; f.norm_cneg = w.norm_cneg;
-    f.row_list = w.fallback_rows; f.n_rows_dev = w.fallback_count; f.n_rows = n;
-    if ((rc = launch_score_exact(f, st)) != PHM_OK) return rc;
+    // rows whose candidate buffer overflowed: exhaustive float64, count read on the device
+    FallbackParams f;
+    f.points = a.points;
+    f.refs = a.refs; f.n_refs = a.n_refs; f.n_positive = a.n_positive;
+    f.cent_pos = a.cent_pos; f.n_cent_pos = a.n_cent_pos; f.cent_neg = a.cent_neg; f.n_cent_neg = a.n_cent_neg;
+    f.rows = w.fallback_rows; f.count = w.fallback_count;
+    f.k_neighbors = a.k_neighbors;
+    f.knn = a.knn; f.kmeans = a.kmeans; f.combo = a.combo;
+    int64_t fb_blocks = n < (int64_t)sm_count() * 4 ? n : (int64_t)sm_count() * 4;
+    score_fallback_kernel<<<(unsigned)fb_blocks, 256, 0, st>>>(f);
+    PHM_CUDA_CHECK(cudaGetLastError());
     if (kernels_launched) *kernels_launched = 7;
     return PHM_OK;
 }
 
-// statistics of the last score_tc call on this workspace: [0] = fallback rows, [1] = max |approx - exact| d2 (as float bits)
-int score_tc_stats(const void *ws, unsigned long long *fallback_rows, float *max_rank_error, cudaStream_t st) {
+// statistics of the last score_tc call on this workspace
+int score_tc_stats(const void *ws, unsigned long long *fallback_rows, float *out3, cudaStream_t st) {
     unsigned char host[256];
     PHM_CUDA_CHECK(cudaMemcpyAsync(host, ws, 256, cudaMemcpyDeviceToHost, st));
     PHM_CUDA_CHECK(cudaStreamSynchronize(st));
     memcpy(fallback_rows, host, 8);
-    memcpy(max_rank_error, host + 64, 8);      // [0] absolute, [1] relative to |a|^2 + |b|^2
+    memcpy(out3, host + 64, 8);                // [0] bound usage (<= 1 proves the interval), [1] largest ranking error in d2 units
     unsigned long long remeasured = 0;
     memcpy(&remeasured, host + 128, 8);
-    max_rank_error[2] = (float)remeasured;     // rows whose mixed neighbour band was re-measured exactly
+    out3[2] = (float)remeasured;               // rows whose neighbour vote needed exact re-measurement
     return PHM_OK;
 }
 

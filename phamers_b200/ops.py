@@ -126,7 +126,8 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3):
                         ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
     if n:
         # both paths: 4 row-preparation kernels (when non-empty) + scorer; the tensor-core path adds re-rank + exact fallback
-        tc_path = dim == 256 and k_neighbors <= 5 and cent_pos.shape[0] and cent_neg.shape[0] and score_path_option != 1
+        tc_path = (dim == 256 and k_neighbors in (1, 3, 5) and refs.shape[0] >= k_neighbors and cent_pos.shape[0]
+                   and cent_neg.shape[0] and score_path_option != 1)
         _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (3 if tc_path else 1))
     return knn, kmeans, combo
 
@@ -142,13 +143,14 @@ def set_score_path(path):
 
 
 def score_stats():
-    """Diagnostics of the last tensor-core score_cuda call: rows re-scored by the exhaustive kernel, rows whose mixed
-    neighbour band was re-measured, and (with _lib.set_option('score_stats', 1)) the largest ranking error."""
+    """Diagnostics of the last tensor-core score_cuda call: rows re-scored by the exhaustive kernel, rows whose vote
+    needed exact re-measurement, and (with _lib.set_option('score_stats', 1)) how much of the proven error interval the
+    true ranking values use (must stay <= 1) and the largest ranking error in squared-distance units."""
     lib = _lib.require_cuda()
     ws = _workspaces[("score", torch.cuda.current_device())]
     rows, err = ctypes.c_uint64(0), (ctypes.c_float * 3)()
     check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
-    return {"fallback_rows": int(rows.value), "max_rank_error": float(err[0]), "max_rank_rel_error": float(err[1]),
+    return {"fallback_rows": int(rows.value), "max_bound_usage": float(err[0]), "max_rank_error": float(err[1]),
             "rows_remeasured": int(err[2])}
 
 

@@ -136,4 +136,4 @@ def test_tensor_core_path_agrees_with_exact_path(scoring):
     assert np.max(np.abs(t_combo[-n_gold:] - g["scores_combo"])) <= TOL
     print("tensor-core path on %d rows: %s" % (len(counts), stats))
     assert stats["fallback_rows"] <= len(counts) // 10
-    assert stats["max_rank_rel_error"] < 2.0 ** -16          # the bound used is 2^-15
+    assert 0.0 < stats["max_bound_usage"] < 0.9              # true ranking values stay inside the proven intervals

@@ -30,7 +30,7 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         st = ops.score_stats()
-        fb, rel = st["fallback_rows"], st["max_rank_rel_error"]
+        fb, rel = st["fallback_rows"], st["max_bound_usage"]
         print("%-34s n=%7d  fallback %7d (%.3f%%)  remeasured %7d  max err %.3g  rel 2^%.1f  %.1f ms"
               % (name, pts.shape[0], fb, 100.0 * fb / pts.shape[0], st["rows_remeasured"], st["max_rank_error"],
                  np.log2(max(rel, 1e-30)), dt * 1e3))
