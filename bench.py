@@ -3,12 +3,18 @@
 bench.py -- the PhaMers hot path (k-mer count -> normalise -> score) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--contigs C] [--k 4]
+                    [--workload shipped|enlarged|count] [--refs R] [--canonical]
 
 A "step" is one pass of the whole hot path over one batch of synthetic contigs: BASELINE.json configs[1]
 ("synthetic metagenome 1M contigs, 1-100 kb lognormal lengths, k=4 tetranucleotide, 1xB200"), scored against the shipped
 phage / bacteria reference features (2255 + 2255 rows, equalised) with the reference's default 'combo' method.
 Scaling is weak: every rank holds its own 1M-contig shard of the same seeded generator (rank r = contigs
 [r*C, (r+1)*C)); the only collective is the all-gather of the per-contig scores.
+
+Other workloads (not the headline; used for DESIGN.md's tables): --workload enlarged = BASELINE configs[4], the same contigs
+scored against R synthetic reference rows (default 1M: shipped rows resampled with Poisson(20000 p) counts, half labelled
+phage), where the tcgen05 distance kernel dominates; --workload count = BASELINE configs[2], counting only for k = 5 / 6 with
+--canonical folding.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel), cpu_baseline (oracle port
 timed on this box's host cores, rank 0, N = 1 only), kernels (per-stage device times), contigs_per_sec.
@@ -36,12 +42,25 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contigs", type=int, default=1000000, help="contigs per GPU")
     ap.add_argument("--k", type=int, default=4)
+    ap.add_argument("--workload", default="shipped", choices=["shipped", "enlarged", "count"])
+    ap.add_argument("--refs", type=int, default=1000000, help="reference rows of --workload enlarged")
+    ap.add_argument("--canonical", action="store_true", help="--workload count: fold reverse complements")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-contigs", type=int, default=800)
     return ap.parse_args()
+
+
+def ncu_traffic():
+    """DRAM bytes measured by ncu --set full for the hot kernels (profiles/traffic.json, committed with the capture it
+    came from); {} when absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
 
 
 def measured_peaks():
@@ -203,25 +222,59 @@ def run_b200(args, rank, local_rank, world):
     n = args.contigs
     seq, offsets = ops.synth_contigs(SEED, rank * n, n)
     bases = int(offsets[-1].item())
+    scoring = args.workload != "count"
+    if scoring and args.k != 4:
+        raise SystemExit("scoring needs k = 4 (the reference features are 256 wide); use --workload count for k = %d" % args.k)
     pos, neg = references.load_reference_features(equalize=True)
     centroids = references.reference_centroids(pos, neg)               # reference-only preprocessing, cached, untimed
-    scorer = pipeline.ContigScorer(pos, neg, centroids=centroids, kmer_length=args.k)
-    n_refs = pos.shape[0] + neg.shape[0]
+    scorer = pipeline.ContigScorer(pos, neg, centroids=centroids, kmer_length=4)
     n_cent = centroids[0].shape[0] + centroids[1].shape[0]
+    if args.workload == "enlarged":
+        # R rows, each a shipped row re-sampled as ~20000 4-mers (Poisson counts), positives first
+        g = torch.Generator(device="cuda")
+        g.manual_seed(SEED)
+        half = args.refs // 2
+        parts = []
+        for src_rows, m in ((pos, half), (neg, args.refs - half)):
+            src_t = torch.from_numpy(src_rows).cuda()
+            pick = torch.randint(0, src_t.shape[0], (m,), generator=g, device="cuda")
+            big = torch.empty((m, 256), dtype=torch.float64, device="cuda")
+            for lo in range(0, m, 1 << 17):
+                lam = (src_t[pick[lo:lo + (1 << 17)]] * 20000.0).float()
+                c = torch.poisson(lam, generator=g).double()
+                big[lo:lo + (1 << 17)] = c / c.sum(dim=1, keepdim=True).clamp_min(1.0)
+            parts.append(big)
+        refs_dev, n_positive = torch.cat(parts), half
+        del parts
+    else:
+        refs_dev, n_positive = scorer.refs, scorer.n_positive
+    n_refs = int(refs_dev.shape[0])
+    _lib.set_option("score_time_kernel", 1)
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     count_ms, score_ms = [], []
 
+    # results are written into buffers allocated once: a production loop scores batch after batch into the same memory, and
+    # allocator calls inside the timed region would only add host noise
+    bins = ops.num_bins(args.k, args.canonical)
+    buf_counts = torch.empty((n, bins), dtype=torch.int32, device="cuda")
+    buf_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda")
+    buf_scores = tuple(torch.empty((n,), dtype=torch.float64, device="cuda") for _ in range(3))
+
     def step(timed):
         e0, e1, e2 = ev(), ev(), ev()
         e0.record(stream)
-        counts, freq = ops.count_cuda(seq, offsets, args.k, counts=True, freq=True)
+        counts, freq = ops.count_cuda(seq, offsets, args.k, canonical=args.canonical, counts=True, freq=True,
+                                      out_counts=buf_counts, out_freq=buf_freq)
         e1.record(stream)
-        knn, km, combo = ops.score_cuda(freq, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)
+        if scoring:
+            knn, km, combo = ops.score_cuda(freq, refs_dev, n_positive, scorer.cent_pos, scorer.cent_neg, 3, out=buf_scores)
+        else:
+            combo = buf_scores[2]
         e2.record(stream)
-        if world > 1:
+        if world > 1 and scoring:
             gathered = parallel.gather_scores(combo, [n] * world)
         else:
             gathered = combo
@@ -233,6 +286,8 @@ def run_b200(args, rank, local_rank, world):
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
+    if scoring:
+        ops.last_kernel_ms("score_tc_kernel")                          # empty the event ring of the warm-up launches
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
@@ -262,16 +317,18 @@ def run_b200(args, rank, local_rank, world):
     elapsed_ms = float(t.item())
     all_bases = float(tot_bases.item())
 
-    score_stats = ops.score_stats() if (args.k == 4 and ops.score_path_option != 1) else None
+    score_stats = ops.score_stats() if (scoring and ops.score_path_option != 1) else None
+    tc_ms = ops.last_kernel_ms("score_tc_kernel") if (scoring and ops.score_path_option != 1) else None
 
     # ---- sanity inside the bench: row sums of the last step's counts (clean synthetic bases) ----
     lengths = offsets[1:] - offsets[:-1]
     assert bool((counts.sum(dim=1, dtype=torch.int64) == lengths - (args.k - 1)).all()), "count row sums are wrong"
-    assert bool(torch.isfinite(gathered).all()) and gathered.numel() == n * world
+    if scoring:
+        assert bool(torch.isfinite(gathered).all()) and gathered.numel() == n * world
 
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.workload == "shipped":
         try:
             host_seq = torch.empty((bases,), dtype=torch.uint8, pin_memory=True)
             host_seq.copy_(seq)
@@ -304,24 +361,31 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline of the dominant kernel (algorithmic work / CUDA-event duration of that kernel) ----
     c_ms = statistics.mean(count_ms)
     s_ms = statistics.mean(score_ms)
-    bins = 4 ** args.k
-    count_bytes = bases * 1.0 + n * bins * 4.0 + n * bins * 8.0        # ASCII read once + u32 counts + f64 features written once
-    score_flops = 2.0 * n * (n_refs + n_cent) * bins
+    # counting stage = ONE kernel launch (+ an 256-byte memset): ASCII read once + u32 counts + f64 features written once
+    count_bytes = bases * 1.0 + n * bins * 4.0 + n * bins * 8.0
+    traffic = ncu_traffic()
     count_roof = {"bound": "hbm", "achieved": count_bytes / (c_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "traffic": None, "kernel": "kmer_hist_kernel", "peak_source": peaks["source"]}
+                  "traffic": traffic.get("kmer_hist_kernel_bytes_per_base", 0) * bases or None,
+                  "kernel": "kmer_hist_kernel", "peak_source": peaks["source"],
+                  "bytes_per_launch": count_bytes, "ms_per_launch": c_ms}
     count_roof["frac"] = count_roof["achieved"] / count_roof["peak"]
-    score_roof = {"bound": "tensor", "achieved": score_flops / (s_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
-                  "unit": "TFLOP/s", "traffic": None, "kernel": "score_tc_kernel (tcgen05 kind::f16, 3 split-FP16 products per algorithmic product) + rerank_kernel",
-                  "peak_source": peaks["source"]}
-    score_roof["frac"] = score_roof["achieved"] / score_roof["peak"]
-    dominant = count_roof if c_ms >= s_ms else score_roof
+    score_roof = None
+    if tc_ms:
+        score_flops = 2.0 * n * (n_refs + n_cent) * 256
+        score_roof = {"bound": "tensor", "achieved": score_flops / (tc_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                      "unit": "TFLOP/s", "traffic": None,
+                      "kernel": "score_tc_kernel (tcgen05 kind::f16, one FP16 product per algorithmic product, FP32 accumulate)",
+                      "peak_source": peaks["source"], "flops_per_launch": score_flops, "ms_per_launch": tc_ms,
+                      "stage_ms": s_ms}
+        score_roof["frac"] = score_roof["achieved"] / score_roof["peak"]
+    dominant = score_roof if (score_roof and tc_ms >= c_ms) else count_roof
 
     # ---- CPU baseline (oracle port, rank 0, N = 1 only, bounded sample) ----
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "shipped":
         from oracle import phamers_oracle as po
         seqs, sample_bases = host_sample(args.cpu_sample_contigs)
         dt = cpu_pass(seqs, pos, neg, None, (centroids[0], centroids[1]))
@@ -335,16 +399,18 @@ def run_b200(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 bases -> u32 counts -> f64 features/scores", "data": "synthetic",
-        "config": {"workload": "synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=%d (BASELINE configs[1]), "
-                               "scored against %d shipped reference rows + %d centroids, method combo"
-                               % (n, args.k, n_refs, n_cent),
+        "config": {"workload": ("synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=%d (BASELINE configs[%s]), "
+                                % (n, args.k, {"shipped": "1", "enlarged": "4", "count": "2"}[args.workload]))
+                               + ("scored against %d %s reference rows + %d centroids, method combo"
+                                  % (n_refs, "shipped" if args.workload == "shipped" else "synthetic", n_cent) if scoring
+                                  else "counting + normalising only%s" % (", canonical bins" if args.canonical else "")),
                    "contigs_per_gpu": n, "bases_per_gpu": bases, "seed": SEED,
                    "l2_policy": "inputs (%.1f GB of bases per step) are far larger than the 126 MB L2" % (bases / 1e9),
                    "parallelism": "contigs sharded over %d GPU(s), references replicated, one NCCL all-gather of scores" % world,
                    "options": args.opt},
         "contigs_per_sec": n * world * args.steps / (elapsed_ms * 1e-3),
-        "kernels": {"count_ms": c_ms, "score_ms": s_ms, "count_roofline": count_roof, "score_roofline": score_roof,
-                    "score_stats": score_stats},
+        "kernels": {"count_ms": c_ms, "score_ms": s_ms, "score_tc_kernel_ms": tc_ms, "count_roofline": count_roof,
+                    "score_roofline": score_roof, "score_stats": score_stats},
         "roofline": dominant, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "device": {"sm": "%d.%d" % (caps.sm_major, caps.sm_minor), "sm_count": caps.sm_count},
     }

@@ -132,8 +132,13 @@ int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max
 
 /* Tuning / path selection for experiments and tests.  Options: "hist_stride_k4" (1 | 2), "hist_contigs_per_item",
  * "score_path" (0 = tensor cores when the shape allows, 1 = exhaustive float64 only, 2 = tensor cores or error),
- * "score_stats" (1 = collect ranking-error diagnostics, slower). */
+ * "score_stats" (1 = collect error-interval diagnostics, slower), "score_time_kernel" (1 = bracket score_tc_kernel with
+ * CUDA events for phm_last_kernel_ms). */
 int phm_set_option(const char *name, int64_t value);
+
+/* Mean device time (ms) of the launches (at most 64) of a hot kernel that is not alone in its entry point since the previous
+ * call; needs the matching option set before the launches ("score_time_kernel" = 1 for "score_tc_kernel").  Synchronises. */
+int phm_last_kernel_ms(const char *kernel, float *ms);
 
 /* ---------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only): contigs with lengths clip(round(exp(N(ln 10000, 1))), 1000,

@@ -43,6 +43,7 @@
 
 namespace phm {
 
+int score_time_kernel = 0;        // option "score_time_kernel": bracket score_tc_kernel with CUDA events (phm_last_kernel_ms)
 int score_debug = 0;              // option "score_debug": timing experiments only (1 = epilogue skips the scan, 2 = scan without hits)
 int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record how much of the bound is used
 
@@ -184,10 +185,14 @@ __device__ __forceinline__ void cand_prune(uint32_t cand_addr, int first, int &c
 }
 
 template <int CAP>
-__device__ __forceinline__ void cand_append(uint32_t cand_addr, int first, int &cnt, bool &overflow, float limit, float lo, int col) {
+__device__ __forceinline__ void cand_append(uint32_t cand_addr, int first, int &cnt, uint32_t &flags, float limit, float lo, int col,
+                                            int label) {
     if (cnt == CAP) cand_prune<CAP>(cand_addr, first, cnt, limit);
     if (cnt == CAP) {
-        overflow = true;                        // more live candidates than slots: the row goes to the exhaustive kernel
+        // More live candidates than slots.  A labelled (reference) candidate is dropped but its label is remembered: the vote
+        // can still be read off when everything that could be among the k nearest -- kept or dropped -- carries one label
+        // (a contig inside a cloud of near-identical references).  Anything else sends the row to the exhaustive kernel.
+        flags |= (label < 0) ? 1u : (2u << label);
     } else {
         sts_v2(cand_addr + (uint32_t)(first + cnt) * (NEPI * 8), __float_as_uint(lo), (uint32_t)col);
         ++cnt;
@@ -209,10 +214,10 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // 
 // 32 accumulator columns of this thread's row (already in registers): lower bounds and their minimum against the row's
 // threshold; only if some lane of the warp has a hit are the hits looked at, one warp-uniform column at a time.
 // INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
-template <int K, int CAP, bool INSERT>
+template <int K, int CAP, bool INSERT, bool LABELLED>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
                                            int n_class, float C, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
-                                           bool &overflow) {
+                                           uint32_t &flags) {
     float lo[32], gm[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -244,8 +249,9 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs
         todo &= todo - 1u;
         const float lo_j = pick32(lo, j);
         if (((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
-            if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(lds_u32(p_c + 4u * j)), lo_j));
-            cand_append<CAP>(cand_addr, first, cnt, overflow, u[K - 1], lo_j, col_c + j);
+            const uint32_t pbits = lds_u32(p_c + 4u * j);        // lowest mantissa bit of P carries the reference's label
+            if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), lo_j));
+            cand_append<CAP>(cand_addr, first, cnt, flags, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
         }
     }
 }
@@ -272,9 +278,9 @@ __device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nb
 // TWO_PASS (first reference tile of a contig tile, centroid tiles): thresholds start at +inf there, so nearly every column
 // would be a hit; instead all 128 upper bounds go through the insertion network first and the hits are collected in a second
 // sweep over the same accumulators (they stay in tensor memory until the set is released).
-template <int K, int CAP, bool TWO_PASS>
+template <int K, int CAP, bool TWO_PASS, bool LABELLED>
 __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C,
-                                          uint32_t cand_addr, int first, float (&u)[K], int &cnt, bool &overflow) {
+                                          uint32_t cand_addr, int first, float (&u)[K], int &cnt, uint32_t &flags) {
     uint32_t ra[32], rb[32];
     __syncwarp();                                      // tcgen05.ld is .sync.aligned: the warp must be converged
     tmem_ld32_issue(taddr, ra);
@@ -294,18 +300,18 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
         tmem_wait_ld();
     }
     tmem_ld32_issue(taddr + 32u, rb);
-    scan_chunk<K, CAP, !TWO_PASS>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, overflow);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, flags);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 64u, ra);
-    scan_chunk<K, CAP, !TWO_PASS>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, overflow);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, flags);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 96u, rb);
-    scan_chunk<K, CAP, !TWO_PASS>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, overflow);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, flags);
     __syncwarp();
     tmem_wait_ld();
-    scan_chunk<K, CAP, !TWO_PASS>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, overflow);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, flags);
 }
 
 struct TcParams {
@@ -318,7 +324,7 @@ struct TcParams {
     const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
     uint2 *cand;                         // [n_points, 16] (lower bound as float bits, column within its class)
     int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
-    uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | overflow << 24
+    uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 overflow, 2 / 4 dropped neg / pos)
 };
 
 template <int KN>
@@ -448,7 +454,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int i = 0; i < KN; ++i) ur[i] = init;
             up[0] = init; un[0] = init;
             int cnt_r = 0, cnt_p = 0, cnt_n = 0;
-            bool overflow = false;
+            uint32_t flags = 0u;                                   // 1 = buffer overflow, 2 / 4 = dropped a negative / positive reference
 
             for (int nt = 0; nt < nt_total; ++nt, ++tile) {
                 const uint32_t set = tile & 1u;
@@ -459,17 +465,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
                 if (p.debug == 1) {
                 } else if (nt == 0)
-                    scan_tile<KN, CAP_R, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, overflow);
+                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags);
                 else if (nt < p.nt_ref)
-                    scan_tile<KN, CAP_R, false>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, overflow);
+                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags);
                 else if (nt == p.nt_ref)
-                    scan_tile<1, CAP_C, true>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, overflow);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags);
                 else if (nt < p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, overflow);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags);
                 else if (nt == p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, true>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, overflow);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags);
                 else
-                    scan_tile<1, CAP_C, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, overflow);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -482,7 +488,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 uint2 *out = p.cand + row * NENT;
 #pragma unroll
                 for (int e = 0; e < NENT; ++e) out[e] = lds_v2(cand_addr + (uint32_t)e * (NEPI * 8));
-                p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (overflow ? (1u << 24) : 0u);
+                p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (flags << 24);
             }
         }
     }
@@ -516,7 +522,7 @@ __device__ __forceinline__ float float_up(double x) {           // a float that 
 // is_ref = 1: reference / centroid rows: FP16 operand, nbs, P, norms, and rho / pmax by atomic max (positive floats order as ints)
 // is_ref = 0: query rows: FP16 operand, norms and C_row (reads rho / pmax, so it must run after every is_ref pass)
 __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
-                                    int is_ref, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
+                                    int is_ref, int64_t n_positive, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
                                     float *__restrict__ nbs, float *__restrict__ pnorm, float *__restrict__ crow,
                                     PrepConsts *consts) {
     const int lane = threadIdx.x & 31;
@@ -556,7 +562,9 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
             const double nH = sqrt(sh) * (1.0 + 1e-12);
             if (is_ref) {
                 nbs[r] = real ? (float)(sc * NORM_SCALE) : PAD_NORM;
-                pnorm[r] = real ? float_up(P) : 0.0f;
+                // P rounded up, bumped past the next even pattern, label (source row < n_positive) in the lowest mantissa bit
+                const uint32_t pb = ((__float_as_uint(float_up(P)) + 2u) & ~1u) | (uint32_t)(sr < n_positive);
+                pnorm[r] = real ? __uint_as_float(pb) : 0.0f;
                 if (real && P > 0.0) {
                     atomicMax(reinterpret_cast<int *>(&consts->rho), __float_as_int(float_up((dB + EPS_ACC * (P + dB)) / P)));
                     atomicMax(reinterpret_cast<int *>(&consts->pmax), __float_as_int(float_up(P)));
@@ -624,7 +632,8 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
             const uint32_t meta = p.meta[row];
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
-            fallback = (meta >> 24) != 0u || cnt_r < kn;
+            const uint32_t flags = meta >> 24;                          // 1 overflow, 2 / 4 dropped a negative / positive reference
+            fallback = (flags & 1u) != 0u || cnt_r < kn;
             const double C = (double)p.crow[row];
             uint2 ent = make_uint2(0u, 0u);
             if (lane < NENT) ent = p.cand[row * NENT + lane];
@@ -656,7 +665,12 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
                 const unsigned band = __ballot_sync(FULL, in_band);
                 const unsigned pos_mask = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
                 const int n_band = __popc(band);
-                if (n_band == kn || pos_mask == 0u || pos_mask == band) {
+                if (flags & 6u) {
+                    // some candidates were dropped: only a unanimous vote over kept AND dropped ones can be read off
+                    if (pos_mask == band && !(flags & 2u)) knn = 1.0;
+                    else if (pos_mask == 0u && !(flags & 4u)) knn = -1.0;
+                    else fallback = true;
+                } else if (n_band == kn || pos_mask == 0u || pos_mask == band) {
                     // the k nearest are exactly the band, or every possible member votes the same way
                     const int pos = (pos_mask == band) ? kn : ((pos_mask == 0u) ? 0 : __popc(pos_mask));
                     knn = (2 * pos > kn) ? 1.0 : -1.0;               // 2 * (predict - 0.5), scripts/learning.py:128
@@ -745,6 +759,7 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
 // overflow: contigs sitting inside a dense cloud of near-identical references), so the grid is small and persistent and
 // reads the row count on the device.
 constexpr int FB_K = 5;
+constexpr int FB_U = 8;                    // reference rows in flight per warp
 struct FallbackParams {
     const double *points;
     const double *refs; int64_t n_refs; int64_t n_positive;
@@ -772,15 +787,37 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
         int bi[FB_K];
 #pragma unroll
         for (int i = 0; i < FB_K; ++i) { bd[i] = INFINITY; bi[i] = -1; }
-        for (int64_t c = warp; c < f.n_refs; c += 8) {          // ascending index per warp: strict '<' keeps the earlier of a tie
-            const double d = warp_exact_d2(x, f.refs + c * KDIM, lane);
+        for (int64_t c0 = warp; c0 < f.n_refs; c0 += 8 * FB_U) {   // ascending index per warp: strict '<' keeps the earlier of a tie
+            double acc[FB_U];
 #pragma unroll
-            for (int i = FB_K - 1; i > 0; --i) {
-                const bool shift = d < bd[i - 1], here = d < bd[i];
-                bi[i] = shift ? bi[i - 1] : (here ? (int)c : bi[i]);
-                bd[i] = shift ? bd[i - 1] : (here ? d : bd[i]);
+            for (int t = 0; t < FB_U; ++t) {                     // FB_U independent rows in flight: this loop is latency-bound
+                const int64_t c = c0 + 8 * t;
+                const double *b = f.refs + (c < f.n_refs ? c : c0) * KDIM;
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) {
+                    const double d = x[i] - b[lane + 32 * i];
+                    a = fma(d, d, a);
+                }
+                acc[t] = a;
             }
-            if (d < bd[0]) { bd[0] = d; bi[0] = (int)c; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int t = 0; t < FB_U; ++t) acc[t] += __shfl_xor_sync(FULL, acc[t], o);
+#pragma unroll
+            for (int t = 0; t < FB_U; ++t) {
+                const int64_t c = c0 + 8 * t;
+                if (c >= f.n_refs) break;
+                const double d = acc[t];
+#pragma unroll
+                for (int i = FB_K - 1; i > 0; --i) {
+                    const bool shift = d < bd[i - 1], here = d < bd[i];
+                    bi[i] = shift ? bi[i - 1] : (here ? (int)c : bi[i]);
+                    bd[i] = shift ? bd[i - 1] : (here ? d : bd[i]);
+                }
+                if (d < bd[0]) { bd[0] = d; bi[0] = (int)c; }
+            }
         }
         double cp = INFINITY, cn = INFINITY;
         for (int64_t c = warp; c < f.n_cent_pos; c += 8) cp = fmin(cp, warp_exact_d2(x, f.cent_pos + c * KDIM, lane));
@@ -900,16 +937,21 @@ bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cp, 
     return dim == KDIM && (k_neighbors == 1 || k_neighbors == 3 || k_neighbors == 5) && n_refs >= k_neighbors && n_cp > 0 && n_cn > 0;
 }
 
-static int launch_prep(const double *src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, __half *op,
+static int launch_prep(const double *src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, int64_t n_positive, __half *op,
                        double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st) {
     if (n_rows == 0) return PHM_OK;
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, is_ref, op, norm64, cnorm64, nbs, pnorm,
+    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
                                                           crow, consts);
     PHM_CUDA_CHECK(cudaGetLastError());
     return PHM_OK;
 }
+
+// brackets of the score_tc_kernel launches since the last phm_last_kernel_ms call (option "score_time_kernel")
+constexpr int EV_RING = 64;
+static cudaEvent_t g_ev[EV_RING][2];
+static int g_ev_made = 0, g_ev_used = 0;
 
 template <int KN>
 static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const TcParams &p, cudaStream_t st) {
@@ -917,8 +959,33 @@ static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const T
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int grid = sm_count();
     if (grid > p.n_mtiles) grid = p.n_mtiles;
+    const bool timed = score_time_kernel && g_ev_used < EV_RING;
+    if (timed) {
+        if (g_ev_made <= g_ev_used) {
+            PHM_CUDA_CHECK(cudaEventCreate(&g_ev[g_ev_used][0]));
+            PHM_CUDA_CHECK(cudaEventCreate(&g_ev[g_ev_used][1]));
+            g_ev_made = g_ev_used + 1;
+        }
+        PHM_CUDA_CHECK(cudaEventRecord(g_ev[g_ev_used][0], st));
+    }
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
     PHM_CUDA_CHECK(cudaGetLastError());
+    if (timed) { PHM_CUDA_CHECK(cudaEventRecord(g_ev[g_ev_used][1], st)); ++g_ev_used; }
+    return PHM_OK;
+}
+
+// mean device time of the bracketed launches, then the ring is emptied
+int score_tc_last_ms(float *ms) {
+    if (g_ev_used == 0) { set_error("no timed score_tc_kernel launch (set option score_time_kernel = 1 first)"); return PHM_E_ARG; }
+    double total = 0.0;
+    for (int i = 0; i < g_ev_used; ++i) {
+        float one = 0.f;
+        PHM_CUDA_CHECK(cudaEventSynchronize(g_ev[i][1]));
+        PHM_CUDA_CHECK(cudaEventElapsedTime(&one, g_ev[i][0], g_ev[i][1]));
+        total += one;
+    }
+    *ms = (float)(total / g_ev_used);
+    g_ev_used = 0;
     return PHM_OK;
 }
 
@@ -939,12 +1006,12 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     while (gcd(perm_a, a.n_refs) != 1) ++perm_a;
     const int64_t perm_c = a.n_refs / 3;
     // references and centroids first (they publish rho and pmax), then the queries
-    if ((rc = launch_prep(a.refs, a.n_refs, ref_pad, perm_a, perm_c, 1, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_pos, a.n_cent_pos, cp_pad, 1, 0, 1, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
+    if ((rc = launch_prep(a.refs, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.cent_pos, a.n_cent_pos, cp_pad, 1, 0, 1, 0, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
                           w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_neg, a.n_cent_neg, cn_pad, 1, 0, 1, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
+    if ((rc = launch_prep(a.cent_neg, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
                           w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.points, n, n, 1, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.points, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
 
     CUtensorMap map_a, map_b;
     if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;

@@ -37,6 +37,14 @@ def _as_u8_cuda(seq):
     return seq
 
 
+def _result(given, shape, dtype):
+    if given is None:
+        return torch.empty(shape, dtype=dtype, device="cuda")
+    if not (given.is_cuda and given.dtype == dtype and tuple(given.shape) == tuple(shape) and given.is_contiguous()):
+        raise TypeError("preallocated result must be a contiguous CUDA %s tensor of shape %s" % (dtype, tuple(shape)))
+    return given
+
+
 def num_bins(k, canonical=False):
     n = _lib.load().phm_num_bins(int(k), _lib.PHM_COUNT_CANONICAL if canonical else 0)
     if n < 0:
@@ -44,10 +52,11 @@ def num_bins(k, canonical=False):
     return int(n)
 
 
-def count_cuda(seq, offsets, k, canonical=False, counts=True, freq=False, naive=False):
+def count_cuda(seq, offsets, k, canonical=False, counts=True, freq=False, naive=False, out_counts=None, out_freq=None):
     """K2+K3.  seq: uint8[total bases] (contigs end to end), offsets: int64[n+1].  Returns (counts int32[n, bins] or
     None, freq float64[n, bins] or None).  Counts are exact unsigned 32-bit values (< 2^31 for any contig this
-    library accepts), stored in an int32 tensor because torch has no first-class uint32."""
+    library accepts), stored in an int32 tensor because torch has no first-class uint32.  out_counts / out_freq: optional
+    preallocated result tensors (int32 / float64 [n, bins]) for callers that score batch after batch."""
     lib = _lib.require_cuda()
     seq = _as_u8_cuda(seq)
     if not (offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()):
@@ -55,8 +64,8 @@ def count_cuda(seq, offsets, k, canonical=False, counts=True, freq=False, naive=
     n = offsets.numel() - 1
     flags = (_lib.PHM_COUNT_CANONICAL if canonical else 0) | (_lib.PHM_COUNT_NAIVE if naive else 0)
     bins = num_bins(k, canonical)
-    out_counts = torch.empty((n, bins), dtype=torch.int32, device="cuda") if (counts or naive) else None
-    out_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda") if freq else None
+    out_counts = _result(out_counts, (n, bins), torch.int32) if (counts or naive) else None
+    out_freq = _result(out_freq, (n, bins), torch.float64) if freq else None
     ws_bytes = lib.phm_kmer_count_workspace_bytes(n, seq.numel(), int(k), flags)
     ws = _workspace("count", ws_bytes)
     check(lib.phm_kmer_count(ptr(seq), ptr(offsets), n, int(k), flags, ptr(out_counts), ptr(out_freq),
@@ -104,9 +113,9 @@ def normalize_cuda(counts):
     return out.reshape(counts.shape)
 
 
-def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3):
+def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=None):
     """K4+K5.  float64 CUDA tensors: points[n, d], refs[R, d] (positives first), centroids[C, d].
-    Returns (knn, kmeans, combo) float64[n]."""
+    Returns (knn, kmeans, combo) float64[n]; out = optional preallocated (knn, kmeans, combo)."""
     lib = _lib.require_cuda()
     tensors = [points, refs, cent_pos, cent_neg]
     for t in tensors:
@@ -116,9 +125,7 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3):
     n, dim = points.shape
     if refs.shape[1] != dim or (cent_pos.numel() and cent_pos.shape[1] != dim) or (cent_neg.numel() and cent_neg.shape[1] != dim):
         raise ValueError("feature widths differ")
-    knn = torch.empty((n,), dtype=torch.float64, device="cuda")
-    kmeans = torch.empty((n,), dtype=torch.float64, device="cuda")
-    combo = torch.empty((n,), dtype=torch.float64, device="cuda")
+    knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
     ws_bytes = lib.phm_score_workspace_bytes(n, refs.shape[0], cent_pos.shape[0], cent_neg.shape[0], dim)
     ws = _workspace("score", ws_bytes)
     check(lib.phm_score(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
@@ -166,3 +173,10 @@ def synth_contigs(seed, first_contig, n_contigs):
     seq = torch.empty(((total + 15) // 16 * 16,), dtype=torch.uint8, device="cuda")
     check(lib.phm_synth_bases(ctypes.c_uint64(seed), int(first_contig), int(n_contigs), ptr(offsets), ptr(seq), stream_ptr()))
     return seq[:total], offsets
+
+
+def last_kernel_ms(kernel="score_tc_kernel"):
+    """Device time of the last launch of a named hot kernel (after _lib.set_option('score_time_kernel', 1))."""
+    ms = ctypes.c_float(0.0)
+    check(_lib.require_cuda().phm_last_kernel_ms(kernel.encode(), ctypes.byref(ms)))
+    return float(ms.value)
