@@ -75,7 +75,7 @@ def measured_peaks():
 
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -86,12 +86,21 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken between the two host times (all samples when none fall inside)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,22 +109,24 @@ class ClockSampler(object):
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, sm_max, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().split("\n"):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                sm_max.append(float(f[2]))
+                rows.append((self._epoch(f[0]), float(f[1]), float(f[2]), float(f[3]),
+                             [name for name, val in zip(names, f[5:9]) if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if r[0] is not None and t_begin is not None and t_begin - 0.02 <= r[0] <= t_end + 0.02]
+        used = inside or rows
+        reasons = sorted({name for r in used for name in r[4]})
+        return {"sm_mhz": statistics.median([r[1] for r in used]) if used else None,
+                "sm_max_mhz": max([r[2] for r in used]) if used else None,
+                "power_w_max": max([r[3] for r in used]) if used else None,
+                "samples": len(used), "samples_inside_timed_region": len(inside), "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -260,17 +271,19 @@ def run_b200(args, rank, local_rank, world):
     # allocator calls inside the timed region would only add host noise
     bins = ops.num_bins(args.k, args.canonical)
     buf_counts = torch.empty((n, bins), dtype=torch.int32, device="cuda")
-    buf_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda")
+    buf_freq = torch.empty((n, bins), dtype=torch.float64, device="cuda") if not scoring else None
     buf_scores = tuple(torch.empty((n,), dtype=torch.float64, device="cuda") for _ in range(3))
 
     def step(timed):
         e0, e1, e2 = ev(), ev(), ev()
         e0.record(stream)
-        counts, freq = ops.count_cuda(seq, offsets, args.k, canonical=args.canonical, counts=True, freq=True,
-                                      out_counts=buf_counts, out_freq=buf_freq)
+        # scoring workloads: stage 2 (normalise) is fused into stage 3 -- the scorer's kernels form count / row total on the
+        # fly (phm_score_counts), so the float64 feature matrix is never written; count-only workloads emit it
+        counts, freq = ops.count_cuda(seq, offsets, args.k, canonical=args.canonical, counts=True, freq=not scoring,
+                                      out_counts=buf_counts, out_freq=buf_freq if not scoring else None)
         e1.record(stream)
         if scoring:
-            knn, km, combo = ops.score_cuda(freq, refs_dev, n_positive, scorer.cent_pos, scorer.cent_neg, 3, out=buf_scores)
+            knn, km, combo = ops.score_cuda(counts, refs_dev, n_positive, scorer.cent_pos, scorer.cent_neg, 3, out=buf_scores)
         else:
             combo = buf_scores[2]
         e2.record(stream)
@@ -283,6 +296,9 @@ def run_b200(args, rank, local_rank, world):
         return counts, gathered
     step.events = []
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                                # running well before the timed region starts
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
@@ -290,12 +306,10 @@ def run_b200(args, rank, local_rank, world):
         ops.last_kernel_ms("score_tc_kernel")                          # empty the event ring of the warm-up launches
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ops.kernel_launches
     t_start, t_end = ev(), ev()
     torch.cuda.synchronize()
+    wall_begin = time.time()
     t_start.record(stream)
     for _ in range(args.steps):
         counts, gathered = step(True)
@@ -303,7 +317,8 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall_end = time.time()
+    clocks = sampler.stop(wall_begin, wall_end) if rank == 0 else None
     launches = ops.kernel_launches - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     for e0, e1, e2 in step.events:
@@ -364,8 +379,9 @@ def run_b200(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel (algorithmic work / CUDA-event duration of that kernel) ----
     c_ms = statistics.mean(count_ms)
     s_ms = statistics.mean(score_ms)
-    # counting stage = ONE kernel launch (+ an 256-byte memset): ASCII read once + u32 counts + f64 features written once
-    count_bytes = bases * 1.0 + n * bins * 4.0 + n * bins * 8.0
+    # counting stage = ONE kernel launch (+ a 256-byte memset): ASCII read once + u32 counts written once;
+    # the count-only workloads also write the float64 features
+    count_bytes = bases * 1.0 + n * bins * 4.0 + (0.0 if scoring else n * bins * 8.0)
     traffic = ncu_traffic()
     count_roof = {"bound": "hbm", "achieved": count_bytes / (c_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "traffic": traffic.get("kmer_hist_kernel_bytes_per_base", 0) * bases or None,
@@ -398,7 +414,7 @@ def run_b200(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8 bases -> u32 counts -> f64 features/scores", "data": "synthetic",
+        "dtype": "u8 bases -> u32 counts -> f64 features (formed in-kernel) -> f64 scores", "data": "synthetic",
         "config": {"workload": ("synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=%d (BASELINE configs[%s]), "
                                 % (n, args.k, {"shipped": "1", "enlarged": "4", "count": "2"}[args.workload]))
                                + ("scored against %d %s reference rows + %d centroids, method combo"
@@ -420,6 +436,9 @@ def run_b200(args, rank, local_rank, world):
 
 
 def main():
+    # NCCL announces its version on STDOUT when the environment asks for NCCL_DEBUG=VERSION/INFO; stdout carries the JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -123,6 +123,16 @@ int phm_score(const double *d_points, int64_t n_points, int dim,
               int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
               void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Stages 2 + 3 fused: same as phm_score, but the queries are the raw uint32 count rows of phm_kmer_count (d_counts[n_points * dim]);
+ * every kernel forms feature = count / row total in float64 on the fly, exactly as kmer.normalize_counts would
+ * (scripts/kmer.py:209-221, scripts/phamer.py:139), so the float64 feature matrix never exists in memory.  Needs the
+ * tensor-core shape (dim = 256, k_neighbors in {1, 3, 5}, both centroid sets), PHM_E_UNSUPPORTED otherwise. */
+int phm_score_counts(const uint32_t *d_counts, int64_t n_points, int dim,
+                     const double *d_refs, int64_t n_refs, int64_t n_positive,
+                     const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+                     int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
+                     void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
  * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
  * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option

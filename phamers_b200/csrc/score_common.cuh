@@ -6,6 +6,7 @@ namespace phm {
 
 struct ScoreArgs {
     const double *points; int64_t n_points; int dim;
+    const uint32_t *point_counts;             // optional: raw count rows instead of `points` (features = row / row sum, formed on the fly)
     const double *refs; int64_t n_refs; int64_t n_positive;
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;

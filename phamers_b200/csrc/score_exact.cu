@@ -222,18 +222,18 @@ extern "C" size_t phm_score_workspace_bytes(int64_t n_points, int64_t n_refs, in
     return exact;
 }
 
-extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
-                         const double *d_refs, int64_t n_refs, int64_t n_positive,
-                         const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
-                         int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
-                         void *d_workspace, size_t workspace_bytes, void *stream) {
+static int score_any(const double *d_points, const uint32_t *d_point_counts, int64_t n_points, int dim,
+                     const double *d_refs, int64_t n_refs, int64_t n_positive,
+                     const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+                     int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
+                     void *d_workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PHM_REQUIRE(n_points >= 0 && dim > 0, "bad query shape");
     PHM_REQUIRE(n_refs >= 1 && n_positive >= 0 && n_positive <= n_refs, "bad reference shape");
     PHM_REQUIRE(k_neighbors >= 1 && k_neighbors <= KNN_MAX && k_neighbors <= n_refs, "k_neighbors must be 1..15 and <= n_refs");
     PHM_REQUIRE(n_cent_pos >= 0 && n_cent_neg >= 0, "bad centroid shape");
     if (n_points == 0) return PHM_OK;
-    PHM_REQUIRE(d_points && d_refs, "null pointer");
+    PHM_REQUIRE((d_points || d_point_counts) && d_refs, "null pointer");
     PHM_REQUIRE((n_cent_pos == 0 || d_cent_pos) && (n_cent_neg == 0 || d_cent_neg), "null centroid pointer");
     PHM_REQUIRE(d_workspace != nullptr, "d_workspace is null");
     if (workspace_bytes < phm_score_workspace_bytes(n_points, n_refs, n_cent_pos, n_cent_neg, dim)) {
@@ -241,7 +241,7 @@ extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
         return PHM_E_WORKSPACE;
     }
     ScoreArgs a;
-    a.points = d_points; a.n_points = n_points; a.dim = dim;
+    a.points = d_points; a.point_counts = d_point_counts; a.n_points = n_points; a.dim = dim;
     a.refs = d_refs; a.n_refs = n_refs; a.n_positive = n_positive;
     a.cent_pos = d_cent_pos; a.n_cent_pos = n_cent_pos;
     a.cent_neg = d_cent_neg; a.n_cent_neg = n_cent_neg;
@@ -252,6 +252,11 @@ extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
     const bool tc_ok = tc::score_tc_supported(dim, k_neighbors, n_refs, n_cent_pos, n_cent_neg);
     if (score_path == 2 && !tc_ok) { set_error("tensor-core scoring needs dim = 256, k_neighbors in {1, 3, 5} and both centroid sets"); return PHM_E_UNSUPPORTED; }
     if (score_path != 1 && tc_ok) return tc::score_tc(a, d_workspace, workspace_bytes, st, nullptr);
+    if (d_point_counts) {
+        set_error("scoring from raw counts needs the tensor-core path (dim = 256, k_neighbors in {1, 3, 5}, both centroid sets); "
+                  "normalise first (phm_normalize_counts) and call phm_score");
+        return PHM_E_UNSUPPORTED;
+    }
 
     double *ws = static_cast<double *>(d_workspace);
     double *np_ = ws, *nr = np_ + n_points, *ncp = nr + n_refs, *ncn = ncp + n_cent_pos;
@@ -262,6 +267,27 @@ extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
     if ((rc = launch_row_norms(d_cent_pos, n_cent_pos, dim, ncp, st)) != PHM_OK) return rc;
     if ((rc = launch_row_norms(d_cent_neg, n_cent_neg, dim, ncn, st)) != PHM_OK) return rc;
     return launch_score_exact(a, st);
+}
+
+extern "C" int phm_score(const double *d_points, int64_t n_points, int dim,
+                         const double *d_refs, int64_t n_refs, int64_t n_positive,
+                         const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+                         int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
+                         void *d_workspace, size_t workspace_bytes, void *stream) {
+    PHM_REQUIRE(d_points != nullptr || n_points == 0, "d_points is null");
+    return score_any(d_points, nullptr, n_points, dim, d_refs, n_refs, n_positive, d_cent_pos, n_cent_pos, d_cent_neg, n_cent_neg,
+                     k_neighbors, d_knn, d_kmeans, d_combo, d_workspace, workspace_bytes, stream);
+}
+
+// Stages 2 + 3 fused: the query features are never materialised, every kernel forms count / row total on the fly.
+extern "C" int phm_score_counts(const uint32_t *d_counts, int64_t n_points, int dim,
+                                const double *d_refs, int64_t n_refs, int64_t n_positive,
+                                const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+                                int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
+                                void *d_workspace, size_t workspace_bytes, void *stream) {
+    PHM_REQUIRE(d_counts != nullptr || n_points == 0, "d_counts is null");
+    return score_any(nullptr, d_counts, n_points, dim, d_refs, n_refs, n_positive, d_cent_pos, n_cent_pos, d_cent_neg, n_cent_neg,
+                     k_neighbors, d_knn, d_kmeans, d_combo, d_workspace, workspace_bytes, stream);
 }
 
 // Diagnostics of the last tensor-core phm_score call that used this workspace (synchronises the stream).

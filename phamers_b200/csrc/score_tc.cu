@@ -500,6 +500,37 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+// RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
+// and q0 + e / b = a / b, so RN(q0 + e r) can only differ from RN(a / b) if a / b lay within 2^-105 (relative) of a rounding
+// boundary; a quotient of such integers is at least 2^-93 away from every midpoint and never on one.  b = 0 (empty contig):
+// r = inf, 0 * inf = NaN, the 0 / 0 of kmer.normalize_counts.  tests/test_gpu_count.py checks it against true division.
+__device__ __forceinline__ double exact_quotient(double a, double b, double r) {
+    const double q0 = a * r;
+    const double e = fma(-q0, b, a);
+    return fma(e, r, q0);
+}
+
+// This lane's 8 features of a query row: from the float64 feature matrix, or from raw counts divided by the row total
+// (IEEE float64 division, exactly what kmer.normalize_counts does, scripts/kmer.py:219-220).
+__device__ __forceinline__ void load_query_row(const double *points, const uint32_t *counts, int64_t row, int lane,
+                                               double (&x)[KDIM / 32]) {
+    if (counts) {
+        uint32_t c[KDIM / 32];
+        unsigned long long total = 0;
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) { c[i] = counts[row * KDIM + lane + 32 * i]; total += c[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+        const double t = (double)total;
+        const double r = 1.0 / t;                        // correctly rounded reciprocal, once per row
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) x[i] = exact_quotient((double)c[i], t, r);
+    } else {
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) x[i] = points[row * KDIM + lane + 32 * i];
+    }
+}
+
 // ---------------- operand preparation: float64 rows -> centred, 2^12-scaled FP16 + exact residual norms ----------------
 // Distances are translation invariant, so every row is shifted by the uniform vector 1/256 before rounding: frequency rows
 // sum to 1, which makes |x - u|^2 = |x|^2 - 1/256 about 4.5x smaller than |x|^2 and shrinks every error term with it.
@@ -522,7 +553,7 @@ __device__ __forceinline__ float float_up(double x) {           // a float that 
 // is_ref = 1: reference / centroid rows: FP16 operand, nbs, P, norms, and rho / pmax by atomic max (positive floats order as ints)
 // is_ref = 0: query rows: FP16 operand, norms and C_row (reads rho / pmax, so it must run after every is_ref pass)
 __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
-                                    int is_ref, int64_t n_positive, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
+                                    const uint32_t *__restrict__ src_counts, int is_ref, int64_t n_positive, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
                                     float *__restrict__ nbs, float *__restrict__ pnorm, float *__restrict__ crow,
                                     PrepConsts *consts) {
     const int lane = threadIdx.x & 31;
@@ -534,8 +565,12 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
     for (int64_t r = warp; r < n_rows; r += n_warps) {
         double s = 0.0, sc = 0.0, sd = 0.0, sh = 0.0;       // |x|^2, |x - u|^2, |B~ - B|^2, |B|^2 (scaled units)
         const int64_t sr = (r < n_src) ? (perm_a * r + perm_c) % n_src : 0;
-        for (int d = lane; d < KDIM; d += 32) {
-            const double x = (r < n_src) ? src[sr * KDIM + d] : shift;
+        double xs[KDIM / 32];
+        if (r < n_src) load_query_row(src, src_counts, sr, lane, xs);
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) {
+            const int d = lane + 32 * i;
+            const double x = (r < n_src) ? xs[i] : shift;
             const double xc = x - shift;
             const double t = xc * (double)SCALE;
             const __half h = __float2half_rn((float)t);
@@ -581,7 +616,7 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
 
 // ---------------- decision: candidates -> vote / centroid distances, exact float64 where it matters ----------------
 struct DecideParams {
-    const double *points; int64_t n_points;
+    const double *points; const uint32_t *point_counts; int64_t n_points;
     const double *refs; int64_t n_refs; int64_t n_positive;
     int64_t perm_a, perm_c;            // reference candidate index -> original row: (perm_a * idx + perm_c) mod n_refs
     const double *cent_pos; int64_t n_cent_pos;
@@ -626,10 +661,8 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
         bool fallback = false;
         double knn = NAN, km = NAN;
         if (!isnan(na)) {
-            const double *pt = p.points + row * KDIM;
             double x[KDIM / 32];
-#pragma unroll
-            for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
+            load_query_row(p.points, p.point_counts, row, lane, x);
             const uint32_t meta = p.meta[row];
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
             const uint32_t flags = meta >> 24;                          // 1 overflow, 2 / 4 dropped a negative / positive reference
@@ -761,7 +794,7 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
 constexpr int FB_K = 5;
 constexpr int FB_U = 8;                    // reference rows in flight per warp
 struct FallbackParams {
-    const double *points;
+    const double *points; const uint32_t *point_counts;
     const double *refs; int64_t n_refs; int64_t n_positive;
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
@@ -779,10 +812,8 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
     const unsigned long long count = *f.count;
     for (unsigned long long it = blockIdx.x; it < count; it += gridDim.x) {
         const int64_t row = f.rows[it];
-        const double *pt = f.points + row * KDIM;
         double x[KDIM / 32];
-#pragma unroll
-        for (int i = 0; i < KDIM / 32; ++i) x[i] = pt[lane + 32 * i];
+        load_query_row(f.points, f.point_counts, row, lane, x);
         double bd[FB_K];
         int bi[FB_K];
 #pragma unroll
@@ -937,12 +968,12 @@ bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cp, 
     return dim == KDIM && (k_neighbors == 1 || k_neighbors == 3 || k_neighbors == 5) && n_refs >= k_neighbors && n_cp > 0 && n_cn > 0;
 }
 
-static int launch_prep(const double *src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, int64_t n_positive, __half *op,
+static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, int64_t n_positive, __half *op,
                        double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st) {
     if (n_rows == 0) return PHM_OK;
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
+    tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, src_counts, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
                                                           crow, consts);
     PHM_CUDA_CHECK(cudaGetLastError());
     return PHM_OK;
@@ -1006,12 +1037,12 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     while (gcd(perm_a, a.n_refs) != 1) ++perm_a;
     const int64_t perm_c = a.n_refs / 3;
     // references and centroids first (they publish rho and pmax), then the queries
-    if ((rc = launch_prep(a.refs, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_pos, a.n_cent_pos, cp_pad, 1, 0, 1, 0, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
+    if ((rc = launch_prep(a.refs, nullptr, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.cent_pos, nullptr, a.n_cent_pos, cp_pad, 1, 0, 1, 0, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
                           w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.cent_neg, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
+    if ((rc = launch_prep(a.cent_neg, nullptr, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
                           w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.points, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
 
     CUtensorMap map_a, map_b;
     if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;
@@ -1033,7 +1064,7 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     if (rc != PHM_OK) return rc;
 
     DecideParams r;
-    r.points = a.points; r.n_points = n;
+    r.points = a.points; r.point_counts = a.point_counts; r.n_points = n;
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
@@ -1051,7 +1082,7 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
 
     // rows whose candidate buffer overflowed: exhaustive float64, count read on the device
     FallbackParams f;
-    f.points = a.points;
+    f.points = a.points; f.point_counts = a.point_counts;
     f.refs = a.refs; f.n_refs = a.n_refs; f.n_positive = a.n_positive;
     f.cent_pos = a.cent_pos; f.n_cent_pos = a.n_cent_pos; f.cent_neg = a.cent_neg; f.n_cent_neg = a.n_cent_neg;
     f.rows = w.fallback_rows; f.count = w.fallback_count;

@@ -115,12 +115,17 @@ def normalize_cuda(counts):
 
 def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=None):
     """K4+K5.  float64 CUDA tensors: points[n, d], refs[R, d] (positives first), centroids[C, d].
+    `points` may also be the int32 count matrix of count_cuda: the features (count / row total) are then formed on the fly
+    inside the kernels and never materialised (tensor-core shapes only).
     Returns (knn, kmeans, combo) float64[n]; out = optional preallocated (knn, kmeans, combo)."""
     lib = _lib.require_cuda()
+    from_counts = points.dtype == torch.int32
     tensors = [points, refs, cent_pos, cent_neg]
-    for t in tensors:
+    for t in tensors[1:] if from_counts else tensors:
         if not (t.is_cuda and t.dtype == torch.float64):
-            raise TypeError("score_cuda takes CUDA float64 tensors")
+            raise TypeError("score_cuda takes CUDA float64 tensors (queries may be int32 counts)")
+    if not points.is_cuda:
+        raise TypeError("score_cuda takes CUDA tensors")
     points, refs, cent_pos, cent_neg = (t.contiguous() for t in tensors)
     n, dim = points.shape
     if refs.shape[1] != dim or (cent_pos.numel() and cent_pos.shape[1] != dim) or (cent_neg.numel() and cent_neg.shape[1] != dim):
@@ -128,9 +133,10 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=
     knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
     ws_bytes = lib.phm_score_workspace_bytes(n, refs.shape[0], cent_pos.shape[0], cent_neg.shape[0], dim)
     ws = _workspace("score", ws_bytes)
-    check(lib.phm_score(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
-                        ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
-                        ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
+    entry = lib.phm_score_counts if from_counts else lib.phm_score
+    check(entry(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
+                ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
+                ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
     if n:
         # both paths: 4 row-preparation kernels (when non-empty) + scorer; the tensor-core path adds re-rank + exact fallback
         tc_path = (dim == 256 and k_neighbors in (1, 3, 5) and refs.shape[0] >= k_neighbors and cent_pos.shape[0]

@@ -37,8 +37,9 @@ class ContigScorer(object):
 
     # -- device resident --------------------------------------------------------------------------------
     def score_device(self, seq, offsets, method="combo", return_counts=True):
-        counts, freq = ops.count_cuda(seq, offsets, self.kmer_length, counts=return_counts, freq=True)
-        knn, kmeans, combo = ops.score_cuda(freq, self.refs, self.n_positive, self.cent_pos, self.cent_neg, self.k_neighbors)
+        # stages 2 + 3 fused: the kernels form count / row total on the fly, the float64 feature matrix is never written
+        counts, _ = ops.count_cuda(seq, offsets, self.kmer_length, counts=True, freq=False)
+        knn, kmeans, combo = ops.score_cuda(counts, self.refs, self.n_positive, self.cent_pos, self.cent_neg, self.k_neighbors)
         return counts, {"knn": knn, "kmeans": kmeans, "combo": combo}[method]
 
     # -- host buffers -----------------------------------------------------------------------------------

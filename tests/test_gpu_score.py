@@ -137,3 +137,29 @@ def test_tensor_core_path_agrees_with_exact_path(scoring):
     print("tensor-core path on %d rows: %s" % (len(counts), stats))
     assert stats["fallback_rows"] <= len(counts) // 10
     assert 0.0 < stats["max_bound_usage"] < 0.9              # true ranking values stay inside the proven intervals
+
+
+def test_scoring_from_counts_equals_scoring_from_features(scoring):
+    """phm_score_counts (stages 2 + 3 fused: count / row total formed inside the kernels) must give bit-identical results
+    to phm_normalize_counts followed by phm_score, including the NaN of an empty contig."""
+    import torch
+    from phamers_b200 import ops
+    g, pos, neg = scoring
+    rng = np.random.default_rng(11)
+    counts = np.vstack((g["query_counts"], rng.integers(0, 90, size=(700, 256)))).astype(np.int64)
+    counts[5, :] = 0
+    d_counts = torch.from_numpy(counts.astype(np.int32)).cuda()
+    refs = torch.from_numpy(np.vstack((pos, neg))).cuda()
+    cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
+    cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
+    feats = ops.normalize_cuda(d_counts)
+    a = [t.cpu().numpy() for t in ops.score_cuda(feats, refs, len(pos), cp, cn, 3)]
+    b = [t.cpu().numpy() for t in ops.score_cuda(d_counts, refs, len(pos), cp, cn, 3)]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert np.isnan(b[2][5])
+    n_gold = len(g["query_counts"])
+    assert np.array_equal(b[0][:n_gold][np.arange(n_gold) != 5], g["scores_knn"][np.arange(n_gold) != 5])
+    # shapes the tensor cores do not take are refused, not silently handled elsewhere
+    with pytest.raises(Exception):
+        ops.score_cuda(d_counts, refs, len(pos), cp, cn, 7)
