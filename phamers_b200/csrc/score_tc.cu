@@ -786,44 +786,86 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
     }
 }
 
-// ---------------- rows the decision kernel could not settle: exhaustive float64, one CTA per row ----------------
+// ---------------- rows the decision kernel could not settle: exhaustive float64 ----------------
 // Direct-difference float64 distance to EVERY reference and centroid (the same arithmetic score_decide_kernel uses for its
-// candidates), 8 warps striding over the columns, k smallest by (distance, index).  The rows are few (candidate-buffer
-// overflow: contigs sitting inside a dense cloud of near-identical references), so the grid is small and persistent and
-// reads the row count on the device.
+// candidates), k smallest by (distance, index).  The rows are few (candidate-buffer overflow with mixed labels: contigs sitting
+// inside a dense cloud of near-identical references), so the grid is small and persistent and reads the row count on the
+// device.  When there are fewer rows than CTAs each row is cut into up to FB_SLICES column slices handled by different CTAs;
+// the last CTA to finish a row (ticket counter) merges the slices.
 constexpr int FB_K = 5;
 constexpr int FB_U = 8;                    // reference rows in flight per warp
+constexpr int FB_SLICES = 16;
+constexpr int FB_GRID = 148 * 4;
+struct FallbackPart { double d[FB_K]; int i[FB_K]; int pad; double cp, cn; };
 struct FallbackParams {
     const double *points; const uint32_t *point_counts;
     const double *refs; int64_t n_refs; int64_t n_positive;
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
     const int64_t *rows; const unsigned long long *count;
+    FallbackPart *parts;                   // [FB_GRID][FB_SLICES], used only while rows < CTAs
+    unsigned int *tickets;                 // [FB_GRID], zero on entry, left zero on exit
     int k_neighbors;
     double *knn, *kmeans, *combo;
 };
 
-__global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
-    __shared__ double s_d[8][FB_K];
-    __shared__ int s_i[8][FB_K];
-    __shared__ double s_c[8][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// merge `n_lists` lists sorted by (distance, index) into the vote / score of one row (one thread)
+__device__ __forceinline__ void fallback_finish(const FallbackParams &f, int64_t row, const FallbackPart *lists, int n_lists) {
     const int kn = f.k_neighbors;
+    int pos = 0, head[FB_SLICES];
+    for (int w = 0; w < n_lists; ++w) head[w] = 0;
+    for (int t = 0; t < kn; ++t) {
+        int best = -1;
+        for (int w = 0; w < n_lists; ++w) {
+            if (head[w] >= FB_K || lists[w].i[head[w]] < 0) continue;
+            if (best < 0 || lists[w].d[head[w]] < lists[best].d[head[best]] ||
+                (lists[w].d[head[w]] == lists[best].d[head[best]] && lists[w].i[head[w]] < lists[best].i[head[best]])) best = w;
+        }
+        if (best < 0) break;
+        pos += lists[best].i[head[best]] < f.n_positive;
+        ++head[best];
+    }
+    const double knn = (2 * pos > kn) ? 1.0 : -1.0;             // scripts/learning.py:128
+    double km = NAN;
+    if (f.n_cent_pos > 0 && f.n_cent_neg > 0) {
+        double e_pos = INFINITY, e_neg = INFINITY;
+        for (int w = 0; w < n_lists; ++w) { e_pos = fmin(e_pos, lists[w].cp); e_neg = fmin(e_neg, lists[w].cn); }
+        e_pos = sqrt(e_pos); e_neg = sqrt(e_neg);
+        km = tanh((e_neg - e_pos) / (e_pos + e_neg));          // scripts/phamer.py:206-209
+    }
+    if (f.knn) f.knn[row] = knn;
+    if (f.kmeans) f.kmeans[row] = km;
+    if (f.combo) f.combo[row] = knn + km;
+}
+
+__global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
+    __shared__ FallbackPart s_part[8];
+    __shared__ FallbackPart s_merged;
+    __shared__ FallbackPart s_all[FB_SLICES];
+    __shared__ unsigned int s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long count = *f.count;
-    for (unsigned long long it = blockIdx.x; it < count; it += gridDim.x) {
-        const int64_t row = f.rows[it];
+    if (count == 0) return;
+    int slices = (int)((unsigned long long)gridDim.x / count);
+    slices = slices < 1 ? 1 : (slices > FB_SLICES ? FB_SLICES : slices);
+    const unsigned long long items = count * (unsigned long long)slices;
+    for (unsigned long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const unsigned long long ridx = it / slices;
+        const int slice = (int)(it % slices);
+        const int64_t row = f.rows[ridx];
+        const int64_t c_lo = f.n_refs * slice / slices, c_hi = f.n_refs * (slice + 1) / slices;
         double x[KDIM / 32];
         load_query_row(f.points, f.point_counts, row, lane, x);
         double bd[FB_K];
         int bi[FB_K];
 #pragma unroll
         for (int i = 0; i < FB_K; ++i) { bd[i] = INFINITY; bi[i] = -1; }
-        for (int64_t c0 = warp; c0 < f.n_refs; c0 += 8 * FB_U) {   // ascending index per warp: strict '<' keeps the earlier of a tie
+        for (int64_t c0 = c_lo + warp; c0 < c_hi; c0 += 8 * FB_U) {   // ascending index per warp: strict '<' keeps the earlier of a tie
             double acc[FB_U];
 #pragma unroll
             for (int t = 0; t < FB_U; ++t) {                     // FB_U independent rows in flight: this loop is latency-bound
                 const int64_t c = c0 + 8 * t;
-                const double *b = f.refs + (c < f.n_refs ? c : c0) * KDIM;
+                const double *b = f.refs + (c < c_hi ? c : c0) * KDIM;
                 double a = 0.0;
 #pragma unroll
                 for (int i = 0; i < KDIM / 32; ++i) {
@@ -839,7 +881,7 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
 #pragma unroll
             for (int t = 0; t < FB_U; ++t) {
                 const int64_t c = c0 + 8 * t;
-                if (c >= f.n_refs) break;
+                if (c >= c_hi) break;
                 const double d = acc[t];
 #pragma unroll
                 for (int i = FB_K - 1; i > 0; --i) {
@@ -851,39 +893,51 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
             }
         }
         double cp = INFINITY, cn = INFINITY;
-        for (int64_t c = warp; c < f.n_cent_pos; c += 8) cp = fmin(cp, warp_exact_d2(x, f.cent_pos + c * KDIM, lane));
-        for (int64_t c = warp; c < f.n_cent_neg; c += 8) cn = fmin(cn, warp_exact_d2(x, f.cent_neg + c * KDIM, lane));
-        __syncthreads();                                        // previous row's merge has finished reading
+        if (slice == 0) {
+            for (int64_t c = warp; c < f.n_cent_pos; c += 8) cp = fmin(cp, warp_exact_d2(x, f.cent_pos + c * KDIM, lane));
+            for (int64_t c = warp; c < f.n_cent_neg; c += 8) cn = fmin(cn, warp_exact_d2(x, f.cent_neg + c * KDIM, lane));
+        }
+        __syncthreads();                                        // previous item's merge has finished reading shared memory
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < FB_K; ++i) { s_d[warp][i] = bd[i]; s_i[warp][i] = bi[i]; }
-            s_c[warp][0] = cp; s_c[warp][1] = cn;
+            for (int i = 0; i < FB_K; ++i) { s_part[warp].d[i] = bd[i]; s_part[warp].i[i] = bi[i]; }
+            s_part[warp].cp = cp; s_part[warp].cn = cn;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int pos = 0, head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int t = 0; t < kn; ++t) {                      // k-way merge of the 8 sorted lists by (distance, index)
-                int best = -1;
-                for (int w = 0; w < 8; ++w) {
-                    if (head[w] >= FB_K || s_i[w][head[w]] < 0) continue;
-                    if (best < 0 || s_d[w][head[w]] < s_d[best][head[best]] ||
-                        (s_d[w][head[w]] == s_d[best][head[best]] && s_i[w][head[w]] < s_i[best][head[best]])) best = w;
+            if (slices == 1) {
+                fallback_finish(f, row, s_part, 8);
+            } else {
+                // this CTA's slice as one sorted list, published for whichever CTA finishes the row last
+                int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int t = 0; t < FB_K; ++t) {
+                    int best = -1;
+                    for (int w = 0; w < 8; ++w) {
+                        if (head[w] >= FB_K || s_part[w].i[head[w]] < 0) continue;
+                        if (best < 0 || s_part[w].d[head[w]] < s_part[best].d[head[best]] ||
+                            (s_part[w].d[head[w]] == s_part[best].d[head[best]] && s_part[w].i[head[w]] < s_part[best].i[head[best]])) best = w;
+                    }
+                    s_merged.d[t] = best < 0 ? INFINITY : s_part[best].d[head[best]];
+                    s_merged.i[t] = best < 0 ? -1 : s_part[best].i[head[best]];
+                    if (best >= 0) ++head[best];
                 }
-                if (best < 0) break;
-                pos += s_i[best][head[best]] < f.n_positive;
-                ++head[best];
+                s_merged.cp = INFINITY; s_merged.cn = INFINITY;
+                for (int w = 0; w < 8; ++w) { s_merged.cp = fmin(s_merged.cp, s_part[w].cp); s_merged.cn = fmin(s_merged.cn, s_part[w].cn); }
+                f.parts[ridx * FB_SLICES + slice] = s_merged;
+                __threadfence();
+                s_ticket = atomicAdd(&f.tickets[ridx], 1u);
+                if (s_ticket == (unsigned)slices - 1) {
+                    __threadfence();
+                    // the other CTAs' slices, read past L1 (they were written by other SMs)
+                    for (int w = 0; w < slices; ++w) {
+                        const FallbackPart *src = f.parts + ridx * FB_SLICES + w;
+                        for (int i = 0; i < FB_K; ++i) { s_all[w].d[i] = __ldcg(&src->d[i]); s_all[w].i[i] = __ldcg(&src->i[i]); }
+                        s_all[w].cp = __ldcg(&src->cp); s_all[w].cn = __ldcg(&src->cn);
+                    }
+                    fallback_finish(f, row, s_all, slices);
+                    f.tickets[ridx] = 0u;                       // ready for the next call
+                }
             }
-            const double knn = (2 * pos > kn) ? 1.0 : -1.0;     // scripts/learning.py:128
-            double km = NAN;
-            if (f.n_cent_pos > 0 && f.n_cent_neg > 0) {
-                double e_pos = INFINITY, e_neg = INFINITY;
-                for (int w = 0; w < 8; ++w) { e_pos = fmin(e_pos, s_c[w][0]); e_neg = fmin(e_neg, s_c[w][1]); }
-                e_pos = sqrt(e_pos); e_neg = sqrt(e_neg);
-                km = tanh((e_neg - e_pos) / (e_pos + e_neg));  // scripts/phamer.py:206-209
-            }
-            if (f.knn) f.knn[row] = knn;
-            if (f.kmeans) f.kmeans[row] = km;
-            if (f.combo) f.combo[row] = knn + km;
         }
     }
 }
@@ -929,6 +983,7 @@ struct TcWorkspace {
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
     double *cnorm_points;
     int64_t *fallback_rows;
+    FallbackPart *fb_parts; unsigned int *fb_tickets;
     size_t bytes;
 };
 
@@ -955,6 +1010,8 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.norm_cneg = reinterpret_cast<double *>(take((size_t)n_cn * 8));
     w.cnorm_points = reinterpret_cast<double *>(take((size_t)n * 8));
     w.fallback_rows = reinterpret_cast<int64_t *>(take((size_t)n * 8));
+    w.fb_parts = reinterpret_cast<FallbackPart *>(take(sizeof(FallbackPart) * FB_GRID * FB_SLICES));
+    w.fb_tickets = reinterpret_cast<unsigned int *>(take(sizeof(unsigned int) * FB_GRID));
     w.bytes = off;
     return w;
 }
@@ -1088,8 +1145,9 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     f.rows = w.fallback_rows; f.count = w.fallback_count;
     f.k_neighbors = a.k_neighbors;
     f.knn = a.knn; f.kmeans = a.kmeans; f.combo = a.combo;
-    int64_t fb_blocks = n < (int64_t)sm_count() * 4 ? n : (int64_t)sm_count() * 4;
-    score_fallback_kernel<<<(unsigned)fb_blocks, 256, 0, st>>>(f);
+    f.parts = w.fb_parts; f.tickets = w.fb_tickets;
+    PHM_CUDA_CHECK(cudaMemsetAsync(w.fb_tickets, 0, sizeof(unsigned int) * FB_GRID, st));
+    score_fallback_kernel<<<FB_GRID, 256, 0, st>>>(f);
     PHM_CUDA_CHECK(cudaGetLastError());
     if (kernels_launched) *kernels_launched = 7;
     return PHM_OK;

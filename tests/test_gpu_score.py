@@ -163,3 +163,55 @@ def test_scoring_from_counts_equals_scoring_from_features(scoring):
     # shapes the tensor cores do not take are refused, not silently handled elsewhere
     with pytest.raises(Exception):
         ops.score_cuda(d_counts, refs, len(pos), cp, cn, 7)
+
+
+def test_full_path_properties_at_scale(scoring):
+    """BASELINE configs[1] shape at a size the GPU finishes in a blink (300k synthetic contigs, 4.8 Gbases): properties that
+    do not need an oracle run of the whole thing -- shard invariance (the multi-GPU layout must not change a single score),
+    the tensor-core path against the exhaustive float64 kernel on a sample of rows, the kNN term being exactly +-1, the
+    centroid term inside tanh's range for this metric, and a small prefix against the CPU oracle end to end."""
+    import torch
+    from phamers_b200 import ops, pipeline, references
+    from oracle import c_oracle
+    g, pos, neg = scoring
+    cents = (np.ascontiguousarray(g["centroids_pos"]), np.ascontiguousarray(g["centroids_neg"]))
+    scorer = pipeline.ContigScorer(pos, neg, centroids=cents)
+    n = 300000
+    seq, off = ops.synth_contigs(20260101, 0, n)
+    counts, combo = scorer.score_device(seq, off)
+    assert ops.score_stats()["fallback_rows"] <= 100                # read before another path reuses the workspace
+    knn, km, combo2 = ops.score_cuda(counts, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)
+    assert torch.equal(combo, combo2)
+    assert bool(((knn == 1.0) | (knn == -1.0)).all())
+    assert float(km.abs().max()) <= np.tanh(1.0) + 1e-12
+    assert torch.equal(combo, knn + km)
+
+    # shard invariance: three uneven shards scored separately give the same bits as the whole
+    pieces = []
+    for lo, hi in ((0, 70001), (70001, 70002), (70002, n)):
+        o = (off[lo:hi + 1] - off[lo]).contiguous()
+        s = seq[int(off[lo]):int(off[hi])]
+        if s.data_ptr() % 16:                                       # the C-ABI wants a 16-byte aligned sequence buffer
+            s = s.clone()
+        pieces.append(scorer.score_device(s, o)[1])
+    assert torch.equal(torch.cat(pieces), combo)
+
+    # a sample of rows through the exhaustive float64 kernel
+    idx = torch.from_numpy(np.random.default_rng(5).choice(n, size=3000, replace=False)).cuda()
+    feats = ops.normalize_cuda(counts[idx].contiguous())
+    try:
+        ops.set_score_path("exact")
+        e_knn, e_km, e_combo = ops.score_cuda(feats, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)
+    finally:
+        ops.set_score_path("auto")
+    assert torch.equal(e_knn, knn[idx])
+    assert float((e_combo - combo[idx]).abs().max()) <= 1e-12
+
+    # a prefix against the CPU oracle, end to end (bit-exact counts, scores within the stated tolerance)
+    m = 200
+    end = int(off[m].item())
+    want_counts = c_oracle.count(seq[:end].cpu().numpy(), off[:m + 1].cpu().numpy(), 4)
+    assert np.array_equal(counts[:m].cpu().numpy().view(np.uint32).astype(np.int64), want_counts)
+    want = po.score_points(po.normalize_counts(want_counts), pos, neg, centroids=cents)
+    got = combo[:m].cpu().numpy()
+    assert np.max(np.abs(got - want)) <= TOL and np.array_equal(np.sign(got), np.sign(want))
