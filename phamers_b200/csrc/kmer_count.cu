@@ -31,6 +31,16 @@ __device__ __forceinline__ Dec decode_chunk(uint4 raw, int lo, int hi) {
     return d;
 }
 
+// RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
+// q0 + e / b = a / b, and a quotient of such integers is never within 2^-93 (relative) of a rounding boundary, so RN(q0 + e r) is
+// the IEEE quotient numpy computes in kmer.normalize_counts (scripts/kmer.py:219-220).  b = 0: r = inf, 0 * inf = NaN = 0 / 0.
+// Checked bit for bit against true division by tests/test_gpu_count.py (features of every golden / random contig).
+__device__ __forceinline__ double exact_quotient(double a, double b, double r) {
+    const double q0 = a * r;
+    const double e = fma(-q0, b, a);
+    return fma(e, r, q0);
+}
+
 template <int K, int STRIDE>
 struct HistCfg {
     static constexpr int W = K + STRIDE - 1;             // window width in bases
@@ -160,13 +170,14 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
             const double dtotal = (double)total;
+            const double rtotal = 1.0 / dtotal;
             __syncwarp();
 
             if (!canonical) {
                 for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
                     const uint32_t v = lds_u32(vst + 4u * y);
                     if (counts) counts[c * Cfg::OUT_BINS + y] = v;
-                    if (freq) freq[c * Cfg::OUT_BINS + y] = (double)v / dtotal;
+                    if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)v, dtotal, rtotal);
                 }
             } else {
                 // reverse-complement fold in place: every bin above its partner adds itself onto the partner
@@ -184,7 +195,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                         const uint32_t v = lds_u32(vst + 4u * y);
                         const int64_t o = c * (int64_t)out_bins + compact_lut[y];
                         if (counts) counts[o] = v;
-                        if (freq) freq[o] = (double)v / dtotal;
+                        if (freq) freq[o] = exact_quotient((double)v, dtotal, rtotal);
                     }
                 }
             }

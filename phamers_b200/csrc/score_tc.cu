@@ -323,6 +323,8 @@ struct TcParams {
     const float *pnorm;                  // same layout: P_j = |B~_j| rounded up, 0 on padding rows
     const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
     uint2 *cand;                         // [n_points, 16] (lower bound as float bits, column within its class)
+    float *cand_up;                      // [n_points, 16] matching upper bounds (lower + 2 C P)
+    int ref_pad, cp_pad;                 // offsets of the centroid classes in nbs / pnorm
     int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
     uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 overflow, 2 / 4 dropped neg / pos)
 };
@@ -486,8 +488,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             cand_prune<CAP_C>(cand_addr, CAP_R + CAP_C, cnt_n, un[0]);
             if (row < p.n_points) {
                 uint2 *out = p.cand + row * NENT;
+                float *out_up = p.cand_up + row * NENT;
 #pragma unroll
-                for (int e = 0; e < NENT; ++e) out[e] = lds_v2(cand_addr + (uint32_t)e * (NEPI * 8));
+                for (int e = 0; e < NENT; ++e) {
+                    const uint2 ent = lds_v2(cand_addr + (uint32_t)e * (NEPI * 8));
+                    const bool used = e < CAP_R ? e < cnt_r : (e < CAP_R + CAP_C ? e - CAP_R < cnt_p : e - CAP_R - CAP_C < cnt_n);
+                    const int64_t pcol = (int64_t)ent.y + (e < CAP_R ? 0 : (e < CAP_R + CAP_C ? p.ref_pad : p.ref_pad + p.cp_pad));
+                    out[e] = ent;
+                    // upper bound with the P of that column (all 16 gathers in flight together, once per contig tile)
+                    out_up[e] = used ? fmaf(2.0f * C, p.pnorm[pcol], __uint_as_float(ent.x)) : INFINITY;
+                }
                 p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (flags << 24);
             }
         }
@@ -621,10 +631,8 @@ struct DecideParams {
     int64_t perm_a, perm_c;            // reference candidate index -> original row: (perm_a * idx + perm_c) mod n_refs
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
-    int64_t ref_pad, cp_pad;           // offsets of the centroid classes in the padded column layout (pnorm)
     const double *cnorm_points;        // centred squared norms of the query rows (NaN = NaN feature row)
-    const float *crow; const float *pnorm;
-    const uint2 *cand; const uint32_t *meta;
+    const uint2 *cand; const float *cand_up; const uint32_t *meta;
     int k_neighbors;
     double *knn, *kmeans, *combo;
     int64_t *fallback_rows; unsigned long long *fallback_count;
@@ -667,20 +675,17 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
             const uint32_t flags = meta >> 24;                          // 1 overflow, 2 / 4 dropped a negative / positive reference
             fallback = (flags & 1u) != 0u || cnt_r < kn;
-            const double C = (double)p.crow[row];
             uint2 ent = make_uint2(0u, 0u);
-            if (lane < NENT) ent = p.cand[row * NENT + lane];
+            float up_f = INFINITY;
+            if (lane < NENT) { ent = p.cand[row * NENT + lane]; up_f = p.cand_up[row * NENT + lane]; }
             const bool is_ref = lane < CAP_R && lane < cnt_r;
             const bool is_pos = lane >= CAP_R && lane < CAP_R + cnt_p && lane < CAP_R + CAP_C;
             const bool is_neg = lane >= CAP_R + CAP_C && lane < CAP_R + CAP_C + cnt_n && lane < NENT;
             const int col = (int)ent.y;
-            int64_t pcol = col;                                        // column in the padded layout of pnorm
-            if (is_pos) pcol += p.ref_pad;
-            if (is_neg) pcol += p.ref_pad + p.cp_pad;
             const bool valid = is_ref || is_pos || is_neg;
-            const double width = valid ? 2.0 * C * (double)p.pnorm[pcol] : 0.0;
             const double lower = valid ? (double)__uint_as_float(ent.x) : INFINITY;
-            const double upper = valid ? lower + width : INFINITY;
+            const double upper = valid ? (double)up_f : INFINITY;
+            const double width = valid ? upper - lower : 0.0;
             int my_idx = col;                                          // index in the caller's arrays
             if (is_ref) my_idx = (int)((p.perm_a * (int64_t)col + p.perm_c) % p.n_refs);
 
@@ -752,22 +757,29 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             }
             // ---------------- nearest centroid of each class ----------------
             if (p.n_cent_pos > 0 && p.n_cent_neg > 0) {
-                double e2[2];
+                double e2[2] = {INFINITY, INFINITY};
+                if (cnt_p < 1 || cnt_n < 1) fallback = true;
+                const double u_p = warp_min_d(is_pos ? upper : INFINITY), u_n = warp_min_d(is_neg ? upper : INFINITY);
+                unsigned rest_p = __ballot_sync(FULL, is_pos && lower <= u_p);
+                unsigned rest_n = __ballot_sync(FULL, is_neg && lower <= u_n);
+                while (rest_p | rest_n) {                              // one candidate of each class per round: both rows in flight
+                    const int sp = rest_p ? __ffs(rest_p) - 1 : 0, sn = rest_n ? __ffs(rest_n) - 1 : 0;
+                    const int ip = __shfl_sync(FULL, my_idx, sp), in_ = __shfl_sync(FULL, my_idx, sn);
+                    const double *bp = p.cent_pos + (int64_t)(rest_p ? ip : 0) * KDIM;
+                    const double *bn = p.cent_neg + (int64_t)(rest_n ? in_ : 0) * KDIM;
+                    double ap = 0.0, an = 0.0;
 #pragma unroll
-                for (int cls = 0; cls < 2; ++cls) {
-                    const bool mine = cls ? is_neg : is_pos;
-                    if ((cls ? cnt_n : cnt_p) < 1) fallback = true;
-                    const double u_1 = warp_min_d(mine ? upper : INFINITY);
-                    const double *cents = cls ? p.cent_neg : p.cent_pos;
-                    unsigned rest = __ballot_sync(FULL, mine && lower <= u_1);
-                    double best = INFINITY;
-                    while (rest) {
-                        const int s = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        const int idx = __shfl_sync(FULL, my_idx, s);
-                        best = fmin(best, warp_exact_d2(x, cents + (int64_t)idx * KDIM, lane));
+                    for (int i = 0; i < KDIM / 32; ++i) {
+                        const double tp = x[i] - bp[lane + 32 * i], tn = x[i] - bn[lane + 32 * i];
+                        ap = fma(tp, tp, ap);
+                        an = fma(tn, tn, an);
                     }
-                    e2[cls] = best;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { ap += __shfl_xor_sync(FULL, ap, o); an += __shfl_xor_sync(FULL, an, o); }
+                    if (rest_p) e2[0] = fmin(e2[0], ap);
+                    if (rest_n) e2[1] = fmin(e2[1], an);
+                    rest_p &= rest_p - 1;
+                    rest_n &= rest_n - 1;
                 }
                 const double e_pos = sqrt(e2[0]), e_neg = sqrt(e2[1]);
                 km = tanh((e_neg - e_pos) / (e_pos + e_neg));          // scripts/phamer.py:206-209
@@ -979,7 +991,7 @@ struct TcWorkspace {
     unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 256-byte header
     __half *a_op, *b_op;
     float *nbs, *pnorm, *crow;
-    uint2 *cand; uint32_t *meta;
+    uint2 *cand; float *cand_up; uint32_t *meta;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
     double *cnorm_points;
     int64_t *fallback_rows;
@@ -1003,6 +1015,7 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.pnorm = reinterpret_cast<float *>(take((size_t)r_pad * 4));
     w.crow = reinterpret_cast<float *>(take((size_t)n * 4));
     w.cand = reinterpret_cast<uint2 *>(take((size_t)n * NENT * 8));
+    w.cand_up = reinterpret_cast<float *>(take((size_t)n * NENT * 4));
     w.meta = reinterpret_cast<uint32_t *>(take((size_t)n * 4));
     w.norm_points = reinterpret_cast<double *>(take((size_t)n * 8));
     w.norm_refs = reinterpret_cast<double *>(take((size_t)n_refs * 8));
@@ -1110,7 +1123,8 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
-    p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.meta = w.meta;
+    p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta;
+    p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
     p.debug = score_debug;
     switch (a.k_neighbors) {
         case 1: rc = launch_tc<1>(map_a, map_b, p, st); break;
@@ -1125,8 +1139,7 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
-    r.ref_pad = ref_pad; r.cp_pad = cp_pad;
-    r.cnorm_points = w.cnorm_points; r.crow = w.crow; r.pnorm = w.pnorm; r.cand = w.cand; r.meta = w.meta;
+    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta;
     r.k_neighbors = a.k_neighbors;
     r.knn = a.knn; r.kmeans = a.kmeans; r.combo = a.combo;
     r.fallback_rows = w.fallback_rows; r.fallback_count = w.fallback_count;
