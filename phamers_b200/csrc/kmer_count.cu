@@ -59,7 +59,7 @@ template <int K, int STRIDE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
                  uint32_t *__restrict__ counts, double *__restrict__ freq,
-                 const uint16_t *__restrict__ rc_lut, const uint16_t *__restrict__ compact_lut, int out_bins,
+                 const uint16_t *__restrict__ rc_lut, const uint16_t *__restrict__ canon_lut, int out_bins,
                  unsigned long long *work_counter, int contigs_per_item) {
     using Cfg = HistCfg<K, STRIDE>;
     constexpr int W = Cfg::W;
@@ -164,6 +164,11 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                     sts_u32(direct + 4u * y, v);
                     total += v;
                 }
+            } else if (Cfg::OUT_BINS >= 128) {
+                for (int i = lane; i < Cfg::OUT_BINS / 4; i += 32) {
+                    const uint4 q = lds_v4(tab + 16u * i);
+                    total += (unsigned long long)q.x + q.y + q.z + q.w;
+                }
             } else {
                 for (int y = lane; y < Cfg::OUT_BINS; y += 32) total += lds_u32(tab + 4u * y);
             }
@@ -180,23 +185,16 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                     if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)v, dtotal, rtotal);
                 }
             } else {
-                // reverse-complement fold in place: every bin above its partner adds itself onto the partner
-                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                // reverse-complement fold as a gather over the compact output bins: bin j is represented by y = canon_lut[j]
+                // (y <= rc(y)) and collects its partner unless it is its own reverse complement; stores are contiguous in j
+                for (int j = lane; j < out_bins; j += 32) {
+                    const uint32_t y = canon_lut[j];
                     const uint32_t r = rc_lut[y];
-                    if (r < (uint32_t)y) {
-                        const uint32_t v = lds_u32(vst + 4u * y);
-                        if (v) red_shared_add(vst + 4u * r, v);
-                    }
-                }
-                __syncwarp();
-                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
-                    const uint32_t r = rc_lut[y];
-                    if ((uint32_t)y <= r) {
-                        const uint32_t v = lds_u32(vst + 4u * y);
-                        const int64_t o = c * (int64_t)out_bins + compact_lut[y];
-                        if (counts) counts[o] = v;
-                        if (freq) freq[o] = exact_quotient((double)v, dtotal, rtotal);
-                    }
+                    uint32_t v = lds_u32(vst + 4u * y);
+                    if (r != y) v += lds_u32(vst + 4u * r);
+                    const int64_t o = c * (int64_t)out_bins + j;
+                    if (counts) counts[o] = v;
+                    if (freq) freq[o] = exact_quotient((double)v, dtotal, rtotal);
                 }
             }
             __syncwarp();
@@ -217,7 +215,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
 // --------------------------------------------------------------------------------------------------
 // canonical look-up tables: rc[y] and compact[y] = rank of min(y, rc(y)) among the self-representing bins
 // --------------------------------------------------------------------------------------------------
-__global__ void canonical_lut_kernel(int k, uint16_t *rc_lut, uint16_t *compact_lut) {
+__global__ void canonical_lut_kernel(int k, uint16_t *rc_lut, uint16_t *compact_lut, uint16_t *canon_lut) {
     __shared__ uint16_t rank[4096];
     const int bins = 1 << (2 * k);
     for (int y = threadIdx.x; y < bins; y += blockDim.x) rc_lut[y] = (uint16_t)revcomp_bin((uint32_t)y, k);
@@ -233,6 +231,7 @@ __global__ void canonical_lut_kernel(int k, uint16_t *rc_lut, uint16_t *compact_
     for (int y = threadIdx.x; y < bins; y += blockDim.x) {
         const uint32_t r = rc_lut[y];
         compact_lut[y] = rank[r < (uint32_t)y ? r : y];
+        if ((uint32_t)y <= r) canon_lut[rank[y]] = (uint16_t)y;      // compact bin -> its representative
     }
 }
 
@@ -445,9 +444,10 @@ kmer_hist_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__re
 struct CountWorkspace {
     unsigned long long *counter;     // 8 bytes (work counter), 256-byte slot
     uint16_t *rc_lut;                // 4096 entries
-    uint16_t *compact_lut;           // 4096 entries
+    uint16_t *compact_lut;           // 4096 entries: bin -> compact canonical bin
+    uint16_t *canon_lut;             // 4096 entries: compact canonical bin -> representative bin
 };
-static constexpr size_t kCountWorkspaceBytes = 256 + 2 * 4096 * sizeof(uint16_t);
+static constexpr size_t kCountWorkspaceBytes = 256 + 3 * 4096 * sizeof(uint16_t);
 
 static CountWorkspace carve(void *ws) {
     CountWorkspace w;
@@ -455,6 +455,7 @@ static CountWorkspace carve(void *ws) {
     w.counter = reinterpret_cast<unsigned long long *>(p);
     w.rc_lut = reinterpret_cast<uint16_t *>(p + 256);
     w.compact_lut = w.rc_lut + 4096;
+    w.canon_lut = w.rc_lut + 8192;
     return w;
 }
 
@@ -533,7 +534,7 @@ static int prepare_count(int64_t n_contigs, int k, uint32_t flags, void *ws, siz
     *rc = nullptr; *compact = nullptr;
     *out_bins = 1 << (2 * k);
     if (flags & PHM_COUNT_CANONICAL) {
-        canonical_lut_kernel<<<1, 1024, 0, st>>>(k, w->rc_lut, w->compact_lut);
+        canonical_lut_kernel<<<1, 1024, 0, st>>>(k, w->rc_lut, w->compact_lut, w->canon_lut);
         PHM_CUDA_CHECK(cudaGetLastError());
         *rc = w->rc_lut; *compact = w->compact_lut;
         *out_bins = (int)canonical_bins(k);
@@ -552,6 +553,7 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
     PHM_REQUIRE((reinterpret_cast<uintptr_t>(d_seq) & 15u) == 0, "d_seq must be 16-byte aligned");
     PHM_REQUIRE(d_counts != nullptr || d_freq != nullptr, "both outputs are null");
 
+    const uint16_t *canon = rc ? w.canon_lut : nullptr;           // compact bin -> representative (the histogram kernel gathers)
     if (flags & PHM_COUNT_NAIVE) {
         PHM_REQUIRE(d_counts != nullptr, "the naive kernel needs d_counts");
         PHM_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, (size_t)n_contigs * out_bins * sizeof(uint32_t), st));
@@ -563,15 +565,15 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
         return PHM_OK;
     }
     switch (k) {
-        case 1: return launch_hist<1, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
-        case 2: return launch_hist<2, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
-        case 3: return launch_hist<3, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+        case 1: return launch_hist<1, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 2: return launch_hist<2, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 3: return launch_hist<3, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
         case 4:
             if (hist_stride_for_k4 == 2)
-                return launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
-            return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
-        case 5: return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
-        case 6: return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, compact, out_bins, w.counter, st);
+                return launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 5: return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 6: return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
     }
     return PHM_E_ARG;
 }
