@@ -133,6 +133,21 @@ int phm_score_counts(const uint32_t *d_counts, int64_t n_points, int dim,
                      int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
                      void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole hot path in one call (k = 4): count -> normalise -> score with the reference's default 'combo' method, i.e. what
+ * scripts/phamer.py:131,139,194 do for one FASTA.  Same arguments as phm_kmer_count (d_seq, d_offsets) and phm_score (references,
+ * centroids, outputs); d_counts (uint32[n_contigs * 256], required) receives the counts.  The histogram kernel emits the scorer's
+ * query operands itself, so neither the feature matrix nor a preparation pass over the counts exists; results are bit-identical
+ * to phm_kmer_count + phm_score_counts.  PHM_E_UNSUPPORTED outside the tensor-core shape (k_neighbors in {1, 3, 5}, both
+ * centroid sets non-empty).
+ * ------------------------------------------------------------------------------------------- */
+size_t phm_count_score_workspace_bytes(int64_t n_contigs, int64_t n_bases, int64_t n_refs, int64_t n_cent_pos, int64_t n_cent_neg);
+int phm_count_score(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_contigs,
+                    const double *d_refs, int64_t n_refs, int64_t n_positive,
+                    const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
+                    int k_neighbors, uint32_t *d_counts, double *d_knn, double *d_kmeans, double *d_combo,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
  * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
  * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option
@@ -142,12 +157,12 @@ int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max
 
 /* Tuning / path selection for experiments and tests.  Options: "hist_stride_k4" (1 | 2), "hist_contigs_per_item",
  * "score_path" (0 = tensor cores when the shape allows, 1 = exhaustive float64 only, 2 = tensor cores or error),
- * "score_stats" (1 = collect error-interval diagnostics, slower), "score_time_kernel" (1 = bracket score_tc_kernel with
- * CUDA events for phm_last_kernel_ms). */
+ * "score_stats" (1 = collect error-interval diagnostics, slower), "time_kernels" (1 = bracket the hot kernels with CUDA
+ * events for phm_last_kernel_ms). */
 int phm_set_option(const char *name, int64_t value);
 
-/* Mean device time (ms) of the launches (at most 64) of a hot kernel that is not alone in its entry point since the previous
- * call; needs the matching option set before the launches ("score_time_kernel" = 1 for "score_tc_kernel").  Synchronises. */
+/* Mean device time (ms) of the launches (at most 64) of a hot kernel ("kmer_hist_kernel", "score_tc_kernel") since the previous
+ * call for that kernel; needs option "time_kernels" = 1 before the launches.  Synchronises on the last of them. */
 int phm_last_kernel_ms(const char *kernel, float *ms);
 
 /* ---------------------------------------------------------------------------------------------

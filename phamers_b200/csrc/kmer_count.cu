@@ -11,7 +11,7 @@
 // every SECOND base (a 5-mer holds two consecutive 4-mers), which halves the number of shared-memory atomics;
 // the 1024-bin 5-mer table is projected back onto the 256 4-mer bins when the contig is finished.  Chunks that
 // hold a non-ATGC byte or a contig boundary take a warp-uniform slow path with an exact per-base blank mask.
-#include "phm_common.cuh"
+#include "score_common.cuh"
 #include "kmer_swar.h"
 
 namespace phm {
@@ -31,16 +31,6 @@ __device__ __forceinline__ Dec decode_chunk(uint4 raw, int lo, int hi) {
     return d;
 }
 
-// RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
-// q0 + e / b = a / b, and a quotient of such integers is never within 2^-93 (relative) of a rounding boundary, so RN(q0 + e r) is
-// the IEEE quotient numpy computes in kmer.normalize_counts (scripts/kmer.py:219-220).  b = 0: r = inf, 0 * inf = NaN = 0 / 0.
-// Checked bit for bit against true division by tests/test_gpu_count.py (features of every golden / random contig).
-__device__ __forceinline__ double exact_quotient(double a, double b, double r) {
-    const double q0 = a * r;
-    const double e = fma(-q0, b, a);
-    return fma(e, r, q0);
-}
-
 template <int K, int STRIDE>
 struct HistCfg {
     static constexpr int W = K + STRIDE - 1;             // window width in bases
@@ -55,12 +45,14 @@ struct HistCfg {
 // --------------------------------------------------------------------------------------------------
 // the histogram kernel
 // --------------------------------------------------------------------------------------------------
-template <int K, int STRIDE, int WARPS>
+// EMIT (k = 4, not canonical): the epilogue also writes the tensor-core scorer's query operands for the contig -- FP16 row, error
+// constant, centred norm -- so that the scoring stage starts without a preparation pass over the counts (phm_count_score).
+template <int K, int STRIDE, int WARPS, bool EMIT>
 __global__ void __launch_bounds__(WARPS * 32)
 kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
                  uint32_t *__restrict__ counts, double *__restrict__ freq,
                  const uint16_t *__restrict__ rc_lut, const uint16_t *__restrict__ canon_lut, int out_bins,
-                 unsigned long long *work_counter, int contigs_per_item) {
+                 unsigned long long *work_counter, int contigs_per_item, tc::QueryEmit emit) {
     using Cfg = HistCfg<K, STRIDE>;
     constexpr int W = Cfg::W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -72,6 +64,8 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
     const uint32_t direct = base + (uint32_t)WARPS * Cfg::ALIGN + (uint32_t)warp * Cfg::DIRECT_BYTES;
     const uint32_t vst = (STRIDE > 1) ? direct : tab;     // where the folded 4^K histogram is staged
     const bool canonical = rc_lut != nullptr;
+    float emit_rho = 0.f, emit_pmax = 0.f;
+    if (EMIT) { emit_rho = emit.consts->rho; emit_pmax = emit.consts->pmax; }
 
     if (Cfg::TAB_BINS >= 128) {
         for (int i = lane; i < Cfg::TAB_BINS / 4; i += 32) sts_v4_zero(tab + 16u * i);
@@ -183,6 +177,26 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                     const uint32_t v = lds_u32(vst + 4u * y);
                     if (counts) counts[c * Cfg::OUT_BINS + y] = v;
                     if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)v, dtotal, rtotal);
+                }
+                if (EMIT) {
+                    // same arithmetic, element order and reduction order as tc_prep_rows_kernel on (count / total)
+                    double s = 0.0, sc = 0.0, sd = 0.0, sh = 0.0;
+#pragma unroll
+                    for (int i = 0; i < Cfg::OUT_BINS / 32; ++i) {
+                        const int y = lane + 32 * i;
+                        const double x = exact_quotient((double)lds_u32(vst + 4u * y), dtotal, rtotal);
+                        emit.op[c * Cfg::OUT_BINS + y] = tc::prep_accumulate(x, s, sc, sd, sh);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sc += __shfl_xor_sync(FULL, sc, o);
+                        sd += __shfl_xor_sync(FULL, sd, o);
+                        sh += __shfl_xor_sync(FULL, sh, o);
+                    }
+                    if (lane == 0) {
+                        emit.cnorm[c] = sc;
+                        emit.crow[c] = tc::query_crow(sc, sd, sh, emit_rho, emit_pmax);
+                    }
                 }
             } else {
                 // reverse-complement fold as a gather over the compact output bins: bin j is represented by y = canon_lut[j]
@@ -459,16 +473,19 @@ static CountWorkspace carve(void *ws) {
     return w;
 }
 
+static EventRing g_hist_ring;        // brackets of the kmer_hist_kernel launches (option "time_kernels")
+int kmer_hist_last_ms(float *ms) { return g_hist_ring.mean_ms(ms); }
+
 int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
 int hist_contigs_per_item = 4;
 
-template <int K, int STRIDE, int WARPS>
+template <int K, int STRIDE, int WARPS, bool EMIT = false>
 static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, double *freq,
                        const uint16_t *rc, const uint16_t *compact, int out_bins, unsigned long long *counter,
-                       cudaStream_t st) {
+                       cudaStream_t st, tc::QueryEmit emit = tc::QueryEmit()) {
     using Cfg = HistCfg<K, STRIDE>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN;
-    auto kern = kmer_hist_kernel<K, STRIDE, WARPS>;
+    auto kern = kmer_hist_kernel<K, STRIDE, WARPS, EMIT>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -477,11 +494,17 @@ static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32
     const int64_t items = (n + hist_contigs_per_item - 1) / hist_contigs_per_item;
     const int64_t need = (items + WARPS - 1) / WARPS;
     if (grid > need) grid = need < 1 ? 1 : need;
+    const bool timed = g_hist_ring.begin(st);
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(seq, off, n, counts, freq, rc, compact, out_bins, counter,
-                                                    hist_contigs_per_item);
+                                                    hist_contigs_per_item, emit);
     PHM_CUDA_CHECK(cudaGetLastError());
+    if (timed) g_hist_ring.end(st);
     return PHM_OK;
 }
+
+// k = 4 histogram that also emits the scorer's query operands (called by phm_count_score)
+int launch_count_emit(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, void *ws, size_t ws_bytes,
+                      tc::QueryEmit emit, cudaStream_t st);
 
 template <int K, int WARPS>
 static int launch_hist_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *off, int64_t n,
@@ -508,6 +531,16 @@ static int64_t canonical_bins(int k) {
     int64_t n = 0;
     for (uint32_t y = 0; y < (1u << (2 * k)); ++y) n += (y <= revcomp_bin(y, k));
     return n;
+}
+
+int launch_count_emit(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, void *ws, size_t ws_bytes,
+                      tc::QueryEmit emit, cudaStream_t st) {
+    PHM_REQUIRE(seq != nullptr && off != nullptr && counts != nullptr && ws != nullptr, "null pointer");
+    PHM_REQUIRE((reinterpret_cast<uintptr_t>(seq) & 15u) == 0, "d_seq must be 16-byte aligned");
+    if (ws_bytes < kCountWorkspaceBytes) { set_error("count workspace too small"); return PHM_E_WORKSPACE; }
+    CountWorkspace w = carve(ws);
+    PHM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 256, st));
+    return launch_hist<4, 2, 8, true>(seq, off, n, counts, nullptr, nullptr, nullptr, 256, w.counter, st, emit);
 }
 
 }  // namespace phm

@@ -14,6 +14,8 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int time_kernels = 0;
+
 static int g_sm_count = 0, g_smem_optin = 0;
 
 static void query_device() {
@@ -38,7 +40,7 @@ extern int hist_contigs_per_item;
 extern int score_path;
 extern int score_collect_stats;
 extern int score_debug;
-extern int score_time_kernel;
+int kmer_hist_last_ms(float *ms);
 
 }  // namespace phm
 
@@ -73,7 +75,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_stride_k4")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k4 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 1 && value <= 4096, "1..4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_path")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 auto, 1 exact, 2 tensor cores"); score_path = (int)value; return PHM_OK; }
-    if (!strcmp(name, "score_time_kernel")) { score_time_kernel = value != 0; return PHM_OK; }
+    if (!strcmp(name, "time_kernels")) { time_kernels = value != 0; return PHM_OK; }
     if (!strcmp(name, "score_debug")) { score_debug = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_stats")) { score_collect_stats = value != 0; return PHM_OK; }
     set_error("unknown option '%s'", name);
@@ -84,6 +86,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
 extern "C" int phm_last_kernel_ms(const char *kernel, float *ms) {
     PHM_REQUIRE(kernel != nullptr && ms != nullptr, "null pointer");
     if (!strcmp(kernel, "score_tc_kernel")) return tc::score_tc_last_ms(ms);
+    if (!strcmp(kernel, "kmer_hist_kernel")) return kmer_hist_last_ms(ms);
     set_error("no timing hook for kernel '%s'", kernel);
     return PHM_E_ARG;
 }

@@ -31,6 +31,39 @@ void set_error(const char *fmt, ...);
 int sm_count();                       // cached multiprocessor count of the current device
 int max_smem_optin();                 // cached opt-in shared memory per block
 
+extern int time_kernels;              // option "time_kernels": hot kernels are bracketed with CUDA events (phm_last_kernel_ms)
+
+// CUDA-event brackets of the launches of one kernel since the last read (bench.py's roofline numerator)
+struct EventRing {
+    static constexpr int CAP = 64;
+    cudaEvent_t ev[CAP][2];
+    int made = 0, used = 0;
+    bool begin(cudaStream_t st) {                      // true if this launch is being timed
+        if (!time_kernels || used >= CAP) return false;
+        if (made <= used) {
+            if (cudaEventCreate(&ev[used][0]) != cudaSuccess || cudaEventCreate(&ev[used][1]) != cudaSuccess) return false;
+            made = used + 1;
+        }
+        return cudaEventRecord(ev[used][0], st) == cudaSuccess;
+    }
+    void end(cudaStream_t st) { cudaEventRecord(ev[used][1], st); ++used; }
+    int mean_ms(float *ms) {                           // mean over the recorded launches, then the ring is emptied
+        if (used == 0) { set_error("no timed launch of this kernel (set option time_kernels = 1 first)"); return PHM_E_ARG; }
+        double total = 0.0;
+        for (int i = 0; i < used; ++i) {
+            float one = 0.f;
+            if (cudaEventSynchronize(ev[i][1]) != cudaSuccess || cudaEventElapsedTime(&one, ev[i][0], ev[i][1]) != cudaSuccess) {
+                set_error("reading a kernel timing event failed");
+                return PHM_E_CUDA;
+            }
+            total += one;
+        }
+        *ms = (float)(total / used);
+        used = 0;
+        return PHM_OK;
+    }
+};
+
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -66,6 +99,17 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void sts_v4_zero(uint32_t addr) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+
+// RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
+// q0 + e / b = a / b, and a quotient of such integers is never within 2^-93 (relative) of a rounding boundary nor on one, so
+// RN(q0 + e r) is the IEEE quotient numpy computes in kmer.normalize_counts (scripts/kmer.py:219-220).  b = 0 (empty contig):
+// r = inf, 0 * inf = NaN = 0 / 0.  Checked bit for bit against true division by tests/test_gpu_count.py and
+// tests/test_gpu_score.py::test_scoring_from_counts_equals_scoring_from_features.
+__device__ __forceinline__ double exact_quotient(double a, double b, double r) {
+    const double q0 = a * r;
+    const double e = fma(-q0, b, a);
+    return fma(e, r, q0);
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {          // splitmix64 finaliser

@@ -43,7 +43,6 @@
 
 namespace phm {
 
-int score_time_kernel = 0;        // option "score_time_kernel": bracket score_tc_kernel with CUDA events (phm_last_kernel_ms)
 int score_debug = 0;              // option "score_debug": timing experiments only (1 = epilogue skips the scan, 2 = scan without hits)
 int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record how much of the bound is used
 
@@ -66,7 +65,8 @@ constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = A_BYTES + NSTAGE * BLOCK_BYTES + CAND_BYTES + STG_BYTES + BAR_BYTES;
 constexpr int NTHREADS = 64 + NEPI;
 constexpr int TMEM_COLS = 512;            // two sets of (2 halves x 128 columns) FP32 accumulators
-constexpr float SCALE = 4096.0f;          // operands are scaled by 2^12 -> accumulator = 2^24 a'.b'
+constexpr float SCALE = (float)PREP_SCALE;  // operands are scaled by 2^12 -> accumulator = 2^24 a'.b'
+static_assert(KDIM == PREP_DIM, "score_common.cuh prepares 256-wide rows");
 constexpr double NORM_SCALE = 8388608.0;  // 2^23: ranking value = 2^23 (|b'|^2 - 2 a'.b')
 constexpr float PAD_NORM = 3.0e38f;
 constexpr double EPS_ACC = 1.0 / 65536.0; // FP32 accumulation allowance relative to |A| |B|
@@ -510,16 +510,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-// RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
-// and q0 + e / b = a / b, so RN(q0 + e r) can only differ from RN(a / b) if a / b lay within 2^-105 (relative) of a rounding
-// boundary; a quotient of such integers is at least 2^-93 away from every midpoint and never on one.  b = 0 (empty contig):
-// r = inf, 0 * inf = NaN, the 0 / 0 of kmer.normalize_counts.  tests/test_gpu_count.py checks it against true division.
-__device__ __forceinline__ double exact_quotient(double a, double b, double r) {
-    const double q0 = a * r;
-    const double e = fma(-q0, b, a);
-    return fma(e, r, q0);
-}
-
 // This lane's 8 features of a query row: from the float64 feature matrix, or from raw counts divided by the row total
 // (IEEE float64 division, exactly what kmer.normalize_counts does, scripts/kmer.py:219-220).
 __device__ __forceinline__ void load_query_row(const double *points, const uint32_t *counts, int64_t row, int lane,
@@ -550,16 +540,6 @@ __device__ __forceinline__ void load_query_row(const double *points, const uint3
 // perm_a ~ 0.618 n_src coprime to n_src.  The shipped tables are sorted by taxonomy, so distances to a contig run in long
 // monotone stretches along the file and the running threshold of the epilogue would be beaten far more often than in an
 // exchangeable order; a golden-ratio stride makes every prefix an even sample of the whole file.
-struct PrepConsts {            // device-resident, written by the reference pass, read by the query pass
-    float rho;                 // max_j (dB_j + eps_acc (P_j + dB_j)) / P_j
-    float pmax;                // max_j P_j
-};
-
-__device__ __forceinline__ float float_up(double x) {           // a float that is >= x (x >= 0)
-    float f = (float)x;
-    return ((double)f >= x) ? f : __uint_as_float(__float_as_uint(f) + 1u);
-}
-
 // is_ref = 1: reference / centroid rows: FP16 operand, nbs, P, norms, and rho / pmax by atomic max (positive floats order as ints)
 // is_ref = 0: query rows: FP16 operand, norms and C_row (reads rho / pmax, so it must run after every is_ref pass)
 __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
@@ -579,17 +559,8 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
         if (r < n_src) load_query_row(src, src_counts, sr, lane, xs);
 #pragma unroll
         for (int i = 0; i < KDIM / 32; ++i) {
-            const int d = lane + 32 * i;
             const double x = (r < n_src) ? xs[i] : shift;
-            const double xc = x - shift;
-            const double t = xc * (double)SCALE;
-            const __half h = __float2half_rn((float)t);
-            const double hv = (double)__half2float(h);
-            op[r * KDIM + d] = h;
-            s = fma(x, x, s);
-            sc = fma(xc, xc, sc);
-            sd = fma(t - hv, t - hv, sd);
-            sh = fma(hv, hv, sh);
+            op[r * KDIM + lane + 32 * i] = prep_accumulate(x, s, sc, sd, sh);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -615,10 +586,7 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
                     atomicMax(reinterpret_cast<int *>(&consts->pmax), __float_as_int(float_up(P)));
                 }
             } else if (real) {
-                // err_j <= dA P_j + nA dB_j + eps_acc nA |B_j| + (FP32 roundings of nbs_j, of nbs_j - acc_j and of the fma)
-                //       <= P_j (dA + nA rho + 2^-21 (pmax + nA))        then 1 % on top for the FP32 arithmetic on the bounds
-                const double c = (dB + nH * (double)rho + (double)(pmax + float_up(nH)) / 2097152.0) * 1.01;
-                crow[sr] = isnan(sc) ? NAN : float_up(c);
+                crow[sr] = query_crow(sc, sd, sh, rho, pmax);
             }
         }
     }
@@ -1049,10 +1017,7 @@ static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_
     return PHM_OK;
 }
 
-// brackets of the score_tc_kernel launches since the last phm_last_kernel_ms call (option "score_time_kernel")
-constexpr int EV_RING = 64;
-static cudaEvent_t g_ev[EV_RING][2];
-static int g_ev_made = 0, g_ev_used = 0;
+static EventRing g_tc_ring;      // brackets of the score_tc_kernel launches (option "time_kernels")
 
 template <int KN>
 static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const TcParams &p, cudaStream_t st) {
@@ -1060,37 +1025,28 @@ static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const T
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int grid = sm_count();
     if (grid > p.n_mtiles) grid = p.n_mtiles;
-    const bool timed = score_time_kernel && g_ev_used < EV_RING;
-    if (timed) {
-        if (g_ev_made <= g_ev_used) {
-            PHM_CUDA_CHECK(cudaEventCreate(&g_ev[g_ev_used][0]));
-            PHM_CUDA_CHECK(cudaEventCreate(&g_ev[g_ev_used][1]));
-            g_ev_made = g_ev_used + 1;
-        }
-        PHM_CUDA_CHECK(cudaEventRecord(g_ev[g_ev_used][0], st));
-    }
+    const bool timed = g_tc_ring.begin(st);
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
     PHM_CUDA_CHECK(cudaGetLastError());
-    if (timed) { PHM_CUDA_CHECK(cudaEventRecord(g_ev[g_ev_used][1], st)); ++g_ev_used; }
+    if (timed) g_tc_ring.end(st);
     return PHM_OK;
 }
 
-// mean device time of the bracketed launches, then the ring is emptied
-int score_tc_last_ms(float *ms) {
-    if (g_ev_used == 0) { set_error("no timed score_tc_kernel launch (set option score_time_kernel = 1 first)"); return PHM_E_ARG; }
-    double total = 0.0;
-    for (int i = 0; i < g_ev_used; ++i) {
-        float one = 0.f;
-        PHM_CUDA_CHECK(cudaEventSynchronize(g_ev[i][1]));
-        PHM_CUDA_CHECK(cudaEventElapsedTime(&one, g_ev[i][0], g_ev[i][1]));
-        total += one;
-    }
-    *ms = (float)(total / g_ev_used);
-    g_ev_used = 0;
-    return PHM_OK;
+int score_tc_last_ms(float *ms) { return g_tc_ring.mean_ms(ms); }
+
+static void ref_permutation(int64_t n_refs, int64_t *perm_a, int64_t *perm_c) {
+    // golden-ratio stride coprime to n_refs (see tc_prep_rows_kernel)
+    int64_t pa = (int64_t)(0.6180339887498949 * (double)n_refs);
+    if (pa < 1) pa = 1;
+    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
+    while (gcd(pa, n_refs) != 1) ++pa;
+    *perm_a = pa;
+    *perm_c = n_refs / 3;
 }
 
-int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int *kernels_launched) {
+// Reference side of a scoring call: workspace header cleared, references and centroids prepared (they publish rho and pmax).
+// `emit` (optional) receives where the query operands belong, for a producer that prepares them itself.
+int score_tc_begin(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, QueryEmit *emit) {
     const int64_t n = a.n_points;
     const int64_t ref_pad = round_up(a.n_refs, BN), cp_pad = round_up(a.n_cent_pos, BN), cn_pad = round_up(a.n_cent_neg, BN);
     const int64_t r_pad = ref_pad + cp_pad + cn_pad;
@@ -1100,19 +1056,36 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
 
     PHM_CUDA_CHECK(cudaMemsetAsync(w.fallback_count, 0, 256, st));
     int rc;
-    // golden-ratio stride coprime to n_refs (see tc_prep_rows_kernel)
-    int64_t perm_a = (int64_t)(0.6180339887498949 * (double)a.n_refs);
-    if (perm_a < 1) perm_a = 1;
-    auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t t = x % y; x = y; y = t; } return x; };
-    while (gcd(perm_a, a.n_refs) != 1) ++perm_a;
-    const int64_t perm_c = a.n_refs / 3;
-    // references and centroids first (they publish rho and pmax), then the queries
+    int64_t perm_a, perm_c;
+    ref_permutation(a.n_refs, &perm_a, &perm_c);
     if ((rc = launch_prep(a.refs, nullptr, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
     if ((rc = launch_prep(a.cent_pos, nullptr, a.n_cent_pos, cp_pad, 1, 0, 1, 0, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
                           w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
     if ((rc = launch_prep(a.cent_neg, nullptr, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
                           w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if ((rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
+    if (emit) { emit->op = w.a_op; emit->crow = w.crow; emit->cnorm = w.cnorm_points; emit->consts = w.consts; }
+    return PHM_OK;
+}
+
+int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int *kernels_launched) {
+    int rc = score_tc_begin(a, ws, ws_bytes, st, nullptr);
+    if (rc != PHM_OK) return rc;
+    if (kernels_launched) *kernels_launched = 7;
+    return score_tc_finish(a, ws, ws_bytes, st, false);
+}
+
+// Query side: operand preparation (unless a producer already filled the QueryEmit buffers), contraction, decision, fallback.
+int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, bool queries_prepared) {
+    const int64_t n = a.n_points;
+    const int64_t ref_pad = round_up(a.n_refs, BN), cp_pad = round_up(a.n_cent_pos, BN), cn_pad = round_up(a.n_cent_neg, BN);
+    const int64_t r_pad = ref_pad + cp_pad + cn_pad;
+    TcWorkspace w = carve_tc(ws, n, r_pad, a.n_refs, a.n_cent_pos, a.n_cent_neg);
+    if (ws_bytes < w.bytes) { set_error("workspace too small: %zu < %zu", ws_bytes, w.bytes); return PHM_E_WORKSPACE; }
+    int rc;
+    int64_t perm_a, perm_c;
+    ref_permutation(a.n_refs, &perm_a, &perm_c);
+    if (!queries_prepared &&
+        (rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
 
     CUtensorMap map_a, map_b;
     if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;
@@ -1162,7 +1135,6 @@ int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int
     PHM_CUDA_CHECK(cudaMemsetAsync(w.fb_tickets, 0, sizeof(unsigned int) * FB_GRID, st));
     score_fallback_kernel<<<FB_GRID, 256, 0, st>>>(f);
     PHM_CUDA_CHECK(cudaGetLastError());
-    if (kernels_launched) *kernels_launched = 7;
     return PHM_OK;
 }
 

@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 _workspaces = {}
+_last_score_ws = ["score"]    # which workspace the last scoring call used (score_stats reads its header)
 kernel_launches = 0          # kernels of libphamers_b200.so launched through this module (bench.py reports it)
 
 
@@ -133,6 +134,7 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=
     knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
     ws_bytes = lib.phm_score_workspace_bytes(n, refs.shape[0], cent_pos.shape[0], cent_neg.shape[0], dim)
     ws = _workspace("score", ws_bytes)
+    _last_score_ws[0] = "score"
     entry = lib.phm_score_counts if from_counts else lib.phm_score
     check(entry(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
                 ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
@@ -143,6 +145,26 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=
                    and cent_neg.shape[0] and score_path_option != 1)
         _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (3 if tc_path else 1))
     return knn, kmeans, combo
+
+
+def count_score_cuda(seq, offsets, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out_counts=None, out=None):
+    """The whole hot path in one call (k = 4): returns (counts int32[n, 256], knn, kmeans, combo float64[n]).
+    Bit-identical to count_cuda followed by score_cuda on the counts; the histogram kernel prepares the scorer's operands."""
+    lib = _lib.require_cuda()
+    seq = _as_u8_cuda(seq)
+    n = offsets.numel() - 1
+    refs, cent_pos, cent_neg = (t.contiguous() for t in (refs, cent_pos, cent_neg))
+    counts = _result(out_counts, (n, 256), torch.int32)
+    knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
+    ws_bytes = lib.phm_count_score_workspace_bytes(n, seq.numel(), refs.shape[0], cent_pos.shape[0], cent_neg.shape[0])
+    ws = _workspace("count_score", ws_bytes)
+    _last_score_ws[0] = "count_score"
+    check(lib.phm_count_score(ptr(seq), ptr(offsets), n, ptr(refs), refs.shape[0], int(n_positive), ptr(cent_pos), cent_pos.shape[0],
+                              ptr(cent_neg), cent_neg.shape[0], int(k_neighbors), ptr(counts), ptr(knn), ptr(kmeans), ptr(combo),
+                              ptr(ws), ws.numel(), stream_ptr()))
+    if n:
+        _launched(3 + 1 + 3)          # 3 reference preparations, histogram (+ operands), contraction, decision, fallback
+    return counts, knn, kmeans, combo
 
 
 score_path_option = 0
@@ -160,7 +182,10 @@ def score_stats():
     needed exact re-measurement, and (with _lib.set_option('score_stats', 1)) how much of the proven error interval the
     true ranking values use (must stay <= 1) and the largest ranking error in squared-distance units."""
     lib = _lib.require_cuda()
-    ws = _workspaces[("score", torch.cuda.current_device())]
+    ws = _workspaces[(_last_score_ws[0], torch.cuda.current_device())]
+    if _last_score_ws[0] == "count_score":           # the scorer's share starts after the (256-byte aligned) count workspace
+        skip = (lib.phm_kmer_count_workspace_bytes(0, 0, 4, 0) + 255) // 256 * 256
+        ws = ws[skip:]
     rows, err = ctypes.c_uint64(0), (ctypes.c_float * 3)()
     check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
     return {"fallback_rows": int(rows.value), "max_bound_usage": float(err[0]), "max_rank_error": float(err[1]),
@@ -182,7 +207,8 @@ def synth_contigs(seed, first_contig, n_contigs):
 
 
 def last_kernel_ms(kernel="score_tc_kernel"):
-    """Device time of the last launch of a named hot kernel (after _lib.set_option('score_time_kernel', 1))."""
+    """Mean device time of the launches of a hot kernel ('kmer_hist_kernel', 'score_tc_kernel') since the last call (after
+    _lib.set_option('time_kernels', 1))."""
     ms = ctypes.c_float(0.0)
     check(_lib.require_cuda().phm_last_kernel_ms(kernel.encode(), ctypes.byref(ms)))
     return float(ms.value)

@@ -37,9 +37,10 @@ class ContigScorer(object):
 
     # -- device resident --------------------------------------------------------------------------------
     def score_device(self, seq, offsets, method="combo", return_counts=True):
-        # stages 2 + 3 fused: the kernels form count / row total on the fly, the float64 feature matrix is never written
-        counts, _ = ops.count_cuda(seq, offsets, self.kmer_length, counts=True, freq=False)
-        knn, kmeans, combo = ops.score_cuda(counts, self.refs, self.n_positive, self.cent_pos, self.cent_neg, self.k_neighbors)
+        # one library call: the histogram kernel also emits the scorer's query operands, the scorer forms count / row total
+        # wherever it needs an exact feature; the float64 feature matrix is never written
+        counts, knn, kmeans, combo = ops.count_score_cuda(seq, offsets, self.refs, self.n_positive, self.cent_pos, self.cent_neg,
+                                                          self.k_neighbors)
         return counts, {"knn": knn, "kmeans": kmeans, "combo": combo}[method]
 
     # -- host buffers -----------------------------------------------------------------------------------
