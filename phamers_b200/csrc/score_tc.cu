@@ -185,14 +185,17 @@ __device__ __forceinline__ void cand_prune(uint32_t cand_addr, int first, int &c
 }
 
 template <int CAP>
-__device__ __forceinline__ void cand_append(uint32_t cand_addr, int first, int &cnt, uint32_t &flags, float limit, float lo, int col,
-                                            int label) {
+__device__ __forceinline__ void cand_append(uint32_t cand_addr, int first, int &cnt, uint32_t &flags, float (&drop_lo)[2], float limit,
+                                            float lo, int col, int label) {
     if (cnt == CAP) cand_prune<CAP>(cand_addr, first, cnt, limit);
     if (cnt == CAP) {
-        // More live candidates than slots.  A labelled (reference) candidate is dropped but its label is remembered: the vote
-        // can still be read off when everything that could be among the k nearest -- kept or dropped -- carries one label
-        // (a contig inside a cloud of near-identical references).  Anything else sends the row to the exhaustive kernel.
-        flags |= (label < 0) ? 1u : (2u << label);
+        // More live candidates than slots.  A labelled (reference) candidate is dropped, but the smallest lower bound dropped
+        // per label is remembered: once the scan is over, a dropped label only matters if that bound still reaches the final
+        // threshold, and then the vote can still be read off when everything that could be among the k nearest -- kept or
+        // dropped -- carries one label (a contig inside a cloud of near-identical references).  Anything else (and any
+        // centroid overflow) sends the row to the exhaustive kernels.
+        if (label < 0) flags |= 1u;
+        else drop_lo[label] = fminf(drop_lo[label], lo);
     } else {
         sts_v2(cand_addr + (uint32_t)(first + cnt) * (NEPI * 8), __float_as_uint(lo), (uint32_t)col);
         ++cnt;
@@ -217,7 +220,7 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // 
 template <int K, int CAP, bool INSERT, bool LABELLED>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
                                            int n_class, float C, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
-                                           uint32_t &flags) {
+                                           uint32_t &flags, float (&drop_lo)[2]) {
     float lo[32], gm[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -251,7 +254,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs
         if (((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
             const uint32_t pbits = lds_u32(p_c + 4u * j);        // lowest mantissa bit of P carries the reference's label
             if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), lo_j));
-            cand_append<CAP>(cand_addr, first, cnt, flags, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
+            cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
         }
     }
 }
@@ -280,7 +283,7 @@ __device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nb
 // sweep over the same accumulators (they stay in tensor memory until the set is released).
 template <int K, int CAP, bool TWO_PASS, bool LABELLED>
 __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C,
-                                          uint32_t cand_addr, int first, float (&u)[K], int &cnt, uint32_t &flags) {
+                                          uint32_t cand_addr, int first, float (&u)[K], int &cnt, uint32_t &flags, float (&drop_lo)[2]) {
     uint32_t ra[32], rb[32];
     __syncwarp();                                      // tcgen05.ld is .sync.aligned: the warp must be converged
     tmem_ld32_issue(taddr, ra);
@@ -300,18 +303,18 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
         tmem_wait_ld();
     }
     tmem_ld32_issue(taddr + 32u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, flags);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 64u, ra);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, flags);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 96u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, flags);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, flags);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
 }
 
 struct TcParams {
@@ -319,6 +322,7 @@ struct TcParams {
     int n_mtiles;
     int nt_ref, nt_pos, nt_neg;          // column tiles of each class (each class padded to a multiple of 128 rows)
     int n_refs, n_cent_pos, n_cent_neg;  // real columns of each class
+    const __half *b_img;                 // reference operand, one 16 KB shared-memory image per (tile, K chunk)
     const float *nbs;                    // [(nt_ref + nt_pos + nt_neg) * 128] 2^23 |b'|^2, PAD_NORM on padding rows
     const float *pnorm;                  // same layout: P_j = |B~_j| rounded up, 0 on padding rows
     const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
@@ -326,12 +330,13 @@ struct TcParams {
     float *cand_up;                      // [n_points, 16] matching upper bounds (lower + 2 C P)
     int ref_pad, cp_pad;                 // offsets of the centroid classes in nbs / pnorm
     int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
-    uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 overflow, 2 / 4 dropped neg / pos)
+    uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 = centroid overflow)
+    float2 *drop_lo;                     // [n_points] smallest lower bound of a dropped negative (.x) / positive (.y) reference
 };
 
 template <int KN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
+score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     const uint32_t sm_a = smem_base;                                   // [half 0..1][chunk 0..3] blocks of 16 KB
@@ -386,7 +391,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int kc = 0; kc < NKC; ++kc) {
                         mbar_wait(bar_b_empty + 8 * bstage, bphase ^ 1u);
                         mbar_expect_tx(bar_b_full + 8 * bstage, BLOCK_BYTES);
-                        tma_load_2d(sm_b + bstage * BLOCK_BYTES, &map_b, bar_b_full + 8 * bstage, kc * BK, nt * BN);
+                        bulk_load(sm_b + bstage * BLOCK_BYTES, p.b_img + ((int64_t)nt * NKC + kc) * (BLOCK_BYTES / 2), BLOCK_BYTES,
+                                  bar_b_full + 8 * bstage);
                         if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
                     }
                     // |b|^2 and P of this tile for the epilogue, once the epilogue has let go of the set (two tiles ago)
@@ -456,7 +462,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int i = 0; i < KN; ++i) ur[i] = init;
             up[0] = init; un[0] = init;
             int cnt_r = 0, cnt_p = 0, cnt_n = 0;
-            uint32_t flags = 0u;                                   // 1 = buffer overflow, 2 / 4 = dropped a negative / positive reference
+            uint32_t flags = 0u;                                   // 1 = a centroid buffer overflowed
+            float drop_lo[2] = {INFINITY, INFINITY};               // smallest lower bound of a dropped negative / positive reference
 
             for (int nt = 0; nt < nt_total; ++nt, ++tile) {
                 const uint32_t set = tile & 1u;
@@ -467,17 +474,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
                 if (p.debug == 1) {
                 } else if (nt == 0)
-                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags);
+                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt < p.nt_ref)
-                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags);
+                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt == p.nt_ref)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt < p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt == p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 else
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -499,6 +506,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     out_up[e] = used ? fmaf(2.0f * C, p.pnorm[pcol], __uint_as_float(ent.x)) : INFINITY;
                 }
                 p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (flags << 24);
+                p.drop_lo[row] = make_float2(drop_lo[0], drop_lo[1]);
             }
         }
     }
@@ -560,7 +568,13 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
 #pragma unroll
         for (int i = 0; i < KDIM / 32; ++i) {
             const double x = (r < n_src) ? xs[i] : shift;
-            op[r * KDIM + lane + 32 * i] = prep_accumulate(x, s, sc, sd, sh);
+            const int d = lane + 32 * i;
+            // queries: row-major [n, 256] (fetched by 2-D TMA); references: the shared-memory image of their 128-row tile,
+            // [tile][K chunk of 64][row][128 B with the 16-byte pieces XOR-swizzled by row & 7], so that a B block is ONE
+            // contiguous 16 KB bulk copy instead of 128 row pieces gathered by a tensor map
+            const int64_t o = is_ref ? ((((r >> 7) * NKC + (d >> 6)) * BM + (r & 127)) * BK + ((((d >> 3) & 7) ^ (int)(r & 7)) << 3) + (d & 7))
+                                     : r * KDIM + d;
+            op[o] = prep_accumulate(x, s, sc, sd, sh);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -600,7 +614,7 @@ struct DecideParams {
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
     const double *cnorm_points;        // centred squared norms of the query rows (NaN = NaN feature row)
-    const uint2 *cand; const float *cand_up; const uint32_t *meta;
+    const uint2 *cand; const float *cand_up; const uint32_t *meta; const float2 *drop_lo;
     int k_neighbors;
     double *knn, *kmeans, *combo;
     int64_t *fallback_rows; unsigned long long *fallback_count;
@@ -641,8 +655,8 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             load_query_row(p.points, p.point_counts, row, lane, x);
             const uint32_t meta = p.meta[row];
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
-            const uint32_t flags = meta >> 24;                          // 1 overflow, 2 / 4 dropped a negative / positive reference
-            fallback = (flags & 1u) != 0u || cnt_r < kn;
+            const float2 dropped = p.drop_lo[row];                      // smallest lower bound of a dropped negative / positive reference
+            fallback = (meta >> 24) != 0u || cnt_r < kn;
             uint2 ent = make_uint2(0u, 0u);
             float up_f = INFINITY;
             if (lane < NENT) { ent = p.cand[row * NENT + lane]; up_f = p.cand_up[row * NENT + lane]; }
@@ -671,10 +685,12 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
                 const unsigned band = __ballot_sync(FULL, in_band);
                 const unsigned pos_mask = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
                 const int n_band = __popc(band);
-                if (flags & 6u) {
-                    // some candidates were dropped: only a unanimous vote over kept AND dropped ones can be read off
-                    if (pos_mask == band && !(flags & 2u)) knn = 1.0;
-                    else if (pos_mask == 0u && !(flags & 4u)) knn = -1.0;
+                const bool lost_neg = (double)dropped.x <= u_k, lost_pos = (double)dropped.y <= u_k;
+                if (lost_neg || lost_pos) {
+                    // a dropped candidate could still be among the k nearest: only a unanimous vote over kept AND dropped ones
+                    // can be read off
+                    if (pos_mask == band && !lost_neg) knn = 1.0;
+                    else if (pos_mask == 0u && !lost_pos) knn = -1.0;
                     else fallback = true;
                 } else if (n_band == kn || pos_mask == 0u || pos_mask == band) {
                     // the k nearest are exactly the band, or every possible member votes the same way
@@ -776,6 +792,7 @@ constexpr int FB_K = 5;
 constexpr int FB_U = 8;                    // reference rows in flight per warp
 constexpr int FB_SLICES = 16;
 constexpr int FB_GRID = 148 * 4;
+constexpr int FB_BLOCKED_MIN = FB_GRID;    // more fallback rows than this: blocked kernel (references streamed once per 32 rows)
 struct FallbackPart { double d[FB_K]; int i[FB_K]; int pad; double cp, cn; };
 struct FallbackParams {
     const double *points; const uint32_t *point_counts;
@@ -825,7 +842,7 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
     __shared__ unsigned int s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long count = *f.count;
-    if (count == 0) return;
+    if (count == 0 || count > FB_BLOCKED_MIN) return;          // many rows: score_fallback_blocked_kernel takes them
     int slices = (int)((unsigned long long)gridDim.x / count);
     slices = slices < 1 ? 1 : (slices > FB_SLICES ? FB_SLICES : slices);
     const unsigned long long items = count * (unsigned long long)slices;
@@ -922,6 +939,123 @@ __global__ void __launch_bounds__(256) score_fallback_kernel(FallbackParams f) {
     }
 }
 
+// Many fallback rows (an enlarged reference set that is a cloud of near-duplicates): 32 rows per CTA share every reference tile,
+// which is staged once in shared memory (transposed, padded: conflict-free for lane = reference), so the references are streamed
+// from HBM once per 32 rows instead of once per row.  Reference distances only ORDER the neighbours here; the centroid distances,
+// whose values reach the score, use the same warp_exact_d2 as every other path.
+constexpr int FBB_ROWS = 32, FBB_TR = 32, FBB_PITCH = FBB_TR + 1;
+constexpr int FBB_SMEM = (FBB_ROWS * KDIM + KDIM * FBB_PITCH) * 8 + FBB_ROWS * FB_K * 12 + 64;
+
+template <int QW>                                                          // rows per warp
+__device__ __forceinline__ void fallback_block(const FallbackParams &f, unsigned long long blk, unsigned long long count,
+                                               double *s_rows, double *s_tile, double *s_d, int *s_i) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kn = f.k_neighbors;
+    __syncthreads();
+    // this warp's rows into shared memory; their lists start empty
+    int64_t my_row[QW];
+    double x[QW][KDIM / 32];
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+        const unsigned long long ridx = blk * (8 * QW) + warp * QW + q;
+        my_row[q] = ridx < count ? f.rows[ridx] : -1;
+        if (my_row[q] >= 0) load_query_row(f.points, f.point_counts, my_row[q], lane, x[q]);
+#pragma unroll
+        for (int i = 0; i < KDIM / 32; ++i) s_rows[(warp * QW + q) * KDIM + lane + 32 * i] = my_row[q] >= 0 ? x[q][i] : 0.0;
+        if (lane < FB_K) { s_d[(warp * QW + q) * FB_K + lane] = INFINITY; s_i[(warp * QW + q) * FB_K + lane] = -1; }
+    }
+    double thr[QW];
+#pragma unroll
+    for (int q = 0; q < QW; ++q) thr[q] = INFINITY;
+    for (int64_t c0 = 0; c0 < f.n_refs; c0 += FBB_TR) {
+        __syncthreads();                                                   // previous tile fully consumed
+        for (int idx = threadIdx.x; idx < FBB_TR * KDIM; idx += 256) {
+            const int r = idx >> 8, d = idx & 255;
+            s_tile[d * FBB_PITCH + r] = (c0 + r < f.n_refs) ? f.refs[(c0 + r) * KDIM + d] : 0.0;
+        }
+        __syncthreads();
+        double acc[QW];
+#pragma unroll
+        for (int q = 0; q < QW; ++q) acc[q] = 0.0;
+        const double *xr = s_rows + warp * QW * KDIM;
+#pragma unroll 4
+        for (int d = 0; d < KDIM; d += 2) {
+            const double b0 = s_tile[d * FBB_PITCH + lane], b1 = s_tile[(d + 1) * FBB_PITCH + lane];
+#pragma unroll
+            for (int q = 0; q < QW; ++q) {
+                const double2 xx = *reinterpret_cast<const double2 *>(xr + q * KDIM + d);
+                const double t0 = xx.x - b0, t1 = xx.y - b1;
+                acc[q] = fma(t0, t0, acc[q]);
+                acc[q] = fma(t1, t1, acc[q]);
+            }
+        }
+        const bool real = c0 + lane < f.n_refs;
+#pragma unroll
+        for (int q = 0; q < QW; ++q) {
+            unsigned hit = __ballot_sync(FULL, real && acc[q] < thr[q]);
+            while (hit) {                                                  // ascending lane = ascending reference index
+                const int src = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const double d = __shfl_sync(FULL, acc[q], src);
+                double *ld = s_d + (warp * QW + q) * FB_K;
+                int *li = s_i + (warp * QW + q) * FB_K;
+                if (lane == 0 && d < ld[kn - 1]) {
+                    int p = kn - 1;
+                    while (p > 0 && ld[p - 1] > d) { ld[p] = ld[p - 1]; li[p] = li[p - 1]; --p; }   // strict: earlier index wins ties
+                    ld[p] = d;
+                    li[p] = (int)(c0 + src);
+                }
+                __syncwarp();
+                thr[q] = ld[kn - 1];
+            }
+        }
+    }
+    // centroids (values reach the score: same arithmetic as everywhere else), then the votes
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+        if (my_row[q] < 0) continue;
+        double cp = INFINITY, cn = INFINITY;
+        for (int64_t c = 0; c < f.n_cent_pos; ++c) cp = fmin(cp, warp_exact_d2(x[q], f.cent_pos + c * KDIM, lane));
+        for (int64_t c = 0; c < f.n_cent_neg; ++c) cn = fmin(cn, warp_exact_d2(x[q], f.cent_neg + c * KDIM, lane));
+        if (lane == 0) {
+            const int *li = s_i + (warp * QW + q) * FB_K;
+            int pos = 0;
+            for (int t = 0; t < kn; ++t) pos += (li[t] >= 0 && li[t] < f.n_positive);
+            const double knn = (2 * pos > kn) ? 1.0 : -1.0;               // scripts/learning.py:128
+            double km = NAN;
+            if (f.n_cent_pos > 0 && f.n_cent_neg > 0) {
+                const double e_pos = sqrt(cp), e_neg = sqrt(cn);
+                km = tanh((e_neg - e_pos) / (e_pos + e_neg));              // scripts/phamer.py:206-209
+            }
+            if (f.knn) f.knn[my_row[q]] = knn;
+            if (f.kmeans) f.kmeans[my_row[q]] = km;
+            if (f.combo) f.combo[my_row[q]] = knn + km;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) score_fallback_blocked_kernel(FallbackParams f) {
+    extern __shared__ __align__(16) unsigned char fbb_raw[];
+    double *s_rows = reinterpret_cast<double *>(fbb_raw);                     // [32][256]
+    double *s_tile = s_rows + FBB_ROWS * KDIM;                                // [256][33]
+    double *s_d = s_tile + KDIM * FBB_PITCH;                                  // [32][FB_K]
+    int *s_i = reinterpret_cast<int *>(s_d + FBB_ROWS * FB_K);                // [32][FB_K]
+    const unsigned long long count = *f.count;
+    if (count <= FB_BLOCKED_MIN) return;
+    // rows per warp chosen so that one wave of CTAs covers all rows when it can (the work per CTA is proportional to its rows)
+    int qw = (int)((count + (unsigned long long)gridDim.x * 8 - 1) / ((unsigned long long)gridDim.x * 8));
+    qw = qw > 4 ? 4 : qw;
+    const unsigned long long n_blocks = (count + 8 * qw - 1) / (8 * qw);
+    for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        switch (qw) {
+            case 1: fallback_block<1>(f, blk, count, s_rows, s_tile, s_d, s_i); break;
+            case 2: fallback_block<2>(f, blk, count, s_rows, s_tile, s_d, s_i); break;
+            case 3: fallback_block<3>(f, blk, count, s_rows, s_tile, s_d, s_i); break;
+            default: fallback_block<4>(f, blk, count, s_rows, s_tile, s_d, s_i); break;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -959,7 +1093,7 @@ struct TcWorkspace {
     unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 256-byte header
     __half *a_op, *b_op;
     float *nbs, *pnorm, *crow;
-    uint2 *cand; float *cand_up; uint32_t *meta;
+    uint2 *cand; float *cand_up; uint32_t *meta; float2 *drop_lo;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
     double *cnorm_points;
     int64_t *fallback_rows;
@@ -985,6 +1119,7 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.cand = reinterpret_cast<uint2 *>(take((size_t)n * NENT * 8));
     w.cand_up = reinterpret_cast<float *>(take((size_t)n * NENT * 4));
     w.meta = reinterpret_cast<uint32_t *>(take((size_t)n * 4));
+    w.drop_lo = reinterpret_cast<float2 *>(take((size_t)n * 8));
     w.norm_points = reinterpret_cast<double *>(take((size_t)n * 8));
     w.norm_refs = reinterpret_cast<double *>(take((size_t)n_refs * 8));
     w.norm_cpos = reinterpret_cast<double *>(take((size_t)n_cp * 8));
@@ -1020,13 +1155,13 @@ static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_
 static EventRing g_tc_ring;      // brackets of the score_tc_kernel launches (option "time_kernels")
 
 template <int KN>
-static int launch_tc(const CUtensorMap &map_a, const CUtensorMap &map_b, const TcParams &p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap &map_a, const TcParams &p, cudaStream_t st) {
     auto kern = score_tc_kernel<KN>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int grid = sm_count();
     if (grid > p.n_mtiles) grid = p.n_mtiles;
     const bool timed = g_tc_ring.begin(st);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, p);
     PHM_CUDA_CHECK(cudaGetLastError());
     if (timed) g_tc_ring.end(st);
     return PHM_OK;
@@ -1087,22 +1222,21 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     if (!queries_prepared &&
         (rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
 
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a;
     if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;
-    if ((rc = make_map(&map_b, w.b_op, r_pad)) != PHM_OK) return rc;
 
     TcParams p;
     p.n_points = n;
     p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
-    p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta;
+    p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo;
     p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
     p.debug = score_debug;
     switch (a.k_neighbors) {
-        case 1: rc = launch_tc<1>(map_a, map_b, p, st); break;
-        case 3: rc = launch_tc<3>(map_a, map_b, p, st); break;
-        case 5: rc = launch_tc<5>(map_a, map_b, p, st); break;
+        case 1: rc = launch_tc<1>(map_a, p, st); break;
+        case 3: rc = launch_tc<3>(map_a, p, st); break;
+        case 5: rc = launch_tc<5>(map_a, p, st); break;
         default: set_error("tensor-core scoring supports k_neighbors 1, 3, 5"); return PHM_E_UNSUPPORTED;
     }
     if (rc != PHM_OK) return rc;
@@ -1112,7 +1246,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
-    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta;
+    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta; r.drop_lo = w.drop_lo;
     r.k_neighbors = a.k_neighbors;
     r.knn = a.knn; r.kmeans = a.kmeans; r.combo = a.combo;
     r.fallback_rows = w.fallback_rows; r.fallback_count = w.fallback_count;
@@ -1133,7 +1267,10 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     f.knn = a.knn; f.kmeans = a.kmeans; f.combo = a.combo;
     f.parts = w.fb_parts; f.tickets = w.fb_tickets;
     PHM_CUDA_CHECK(cudaMemsetAsync(w.fb_tickets, 0, sizeof(unsigned int) * FB_GRID, st));
-    score_fallback_kernel<<<FB_GRID, 256, 0, st>>>(f);
+    score_fallback_kernel<<<FB_GRID, 256, 0, st>>>(f);                 // few rows: column slices across CTAs
+    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_CUDA_CHECK(cudaFuncSetAttribute(score_fallback_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FBB_SMEM));
+    score_fallback_blocked_kernel<<<sm_count(), 256, FBB_SMEM, st>>>(f);   // many rows: 32 per CTA share the reference stream
     PHM_CUDA_CHECK(cudaGetLastError());
     return PHM_OK;
 }

@@ -215,3 +215,42 @@ def test_full_path_properties_at_scale(scoring):
     want = po.score_points(po.normalize_counts(want_counts), pos, neg, centroids=cents)
     got = combo[:m].cpu().numpy()
     assert np.max(np.abs(got - want)) <= TOL and np.array_equal(np.sign(got), np.sign(want))
+
+
+@pytest.mark.parametrize("n_rows", [300, 2500])
+def test_fallback_kernels_match_exact_path(scoring, n_rows):
+    """Both exhaustive fallback kernels (column slices across CTAs for few rows, 32 rows per CTA sharing the reference stream
+    for many) against the exhaustive float64 scorer: the debug option makes the tensor-core epilogue keep no candidates, so
+    every row goes down the fallback road."""
+    import torch
+    from phamers_b200 import _lib, ops, references
+    g, pos, neg = scoring
+    rng = np.random.default_rng(n_rows)
+    _, pos_c, _, neg_c = references.load_reference_counts()
+    both = np.vstack((pos_c, neg_c)).astype(np.float64)
+    rows = []
+    for _ in range(n_rows - 1):
+        src = both[int(rng.integers(0, both.shape[0]))]
+        rows.append(rng.multinomial(12000, src / src.sum()))
+    rows.append(np.zeros(256, dtype=np.int64))                            # one empty contig
+    counts = torch.from_numpy(np.stack(rows).astype(np.int32)).cuda()
+    refs = torch.from_numpy(np.vstack((pos, neg))).cuda()
+    cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
+    cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
+    try:
+        _lib.set_option("score_debug", 1)
+        f_knn, f_km, f_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
+        assert ops.score_stats()["fallback_rows"] == n_rows - 1          # the NaN row never asks for a fallback
+    finally:
+        _lib.set_option("score_debug", 0)
+    t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
+    try:
+        ops.set_score_path("exact")
+        e_knn, e_km, e_combo = [t.cpu().numpy() for t in ops.score_cuda(ops.normalize_cuda(counts), refs, len(pos), cp, cn, 3)]
+    finally:
+        ops.set_score_path("auto")
+    ok = ~np.isnan(e_combo)
+    assert ok.sum() == n_rows - 1 and np.isnan(f_combo[-1]) and np.isnan(t_combo[-1])
+    assert np.array_equal(f_knn[ok], e_knn[ok]) and np.array_equal(t_knn[ok], e_knn[ok])
+    assert np.max(np.abs(f_km[ok] - e_km[ok])) <= 1e-12
+    assert np.array_equal(f_km[ok], t_km[ok])                            # centroid term: same arithmetic on every path
