@@ -246,13 +246,25 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs
     const uint32_t hits = __brev(~miss);
     // make room once for the whole warp (one uniform pass) instead of lane by lane inside the loop
     if (__any_sync(FULL, cnt + __popc(hits) > CAP)) cand_prune<CAP>(cand_addr, first, cnt, limit0);
-    uint32_t todo = __reduce_or_sync(FULL, hits);
+    // Common case: a lane's only hit is its minimum, whose value it already holds -- all such lanes are served at once.
+    // Lanes with several hits in the chunk take the column-by-column loop below (warp-uniform column, value picked from the
+    // registers by a compile-time switch).
+    const int n_hits = __popc(hits);
+    if (n_hits == 1) {
+        const int j = __ffs(hits) - 1;
+        if (m <= u[K - 1] && col_c + j < n_class) {
+            const uint32_t pbits = lds_u32(p_c + 4u * j);        // lowest mantissa bit of P carries the reference's label
+            if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), m));
+            cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], m, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
+        }
+    }
+    uint32_t todo = __reduce_or_sync(FULL, n_hits > 1 ? hits : 0u);
     while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1u;
         const float lo_j = pick32(lo, j);
-        if (((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
-            const uint32_t pbits = lds_u32(p_c + 4u * j);        // lowest mantissa bit of P carries the reference's label
+        if (n_hits > 1 && ((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
+            const uint32_t pbits = lds_u32(p_c + 4u * j);
             if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), lo_j));
             cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
         }
