@@ -197,3 +197,31 @@ def test_properties_at_scale():
     seq2, off2 = ops.synth_contigs(20260101, 100, 50)
     a0, a1 = int(off[100].item()), int(off[150].item())
     assert torch.equal(seq2, seq[a0:a1])
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_every_k4_window_stride_matches_oracle(stride):
+    """k = 4 histogram variants (plain 4-mers; 5-mers at every second base) on dirty, clean and awkward workloads: contigs at
+    every alignment, a 700 kb contig, a 300 kb homopolymer (one bin takes every count) and a contig just past 192 kb."""
+    from phamers_b200 import ops, _lib
+    rng = np.random.default_rng(77)
+    seq_a, off_a = _random_workload(rng, 1500, True)
+    seq_b, off_b = _random_workload(rng, 1500, False)
+    lengths = np.array([17, 0, 1, 3, 4, 5, 6, 16, 15, 31, 33, 0, 64, 1000, 7, 511, 513, 2, 700001, 300000, 9, 196608 + 5], dtype=np.int64)
+    off_c = np.concatenate(([0], np.cumsum(lengths)))
+    seq_c = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(off_c[-1]))
+    seq_c[off_c[18] + 350000] = ord("N")
+    seq_c[off_c[19]:off_c[20]] = ord("A")
+    seq_c[off_c[19] + 123457] = ord("c")
+    _lib.set_option("hist_stride_k4", stride)
+    try:
+        for seq, off in ((seq_a, off_a), (seq_b, off_b), (seq_c, off_c)):
+            d_seq, d_off = _device(seq, off)
+            want = c_oracle.count(seq, off, 4)
+            counts, freq = ops.count_cuda(d_seq, d_off, 4, freq=True)
+            assert np.array_equal(_u32(counts), want)
+            assert np.array_equal(freq.cpu().numpy(), c_oracle.normalize(want), equal_nan=True)
+            canon, _ = ops.count_cuda(d_seq, d_off, 4, canonical=True)
+            assert np.array_equal(_u32(canon), po.canonical_fold(want, 4))
+    finally:
+        _lib.set_option("hist_stride_k4", 2)
