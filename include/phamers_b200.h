@@ -152,10 +152,12 @@ int phm_count_score(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_co
  * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
  * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option
  * "score_stats" is 1), stats[1] = largest |ranking value - exact| in squared-distance units (same condition), stats[2] =
- * rows whose neighbour vote needed exact re-measurement.  The caller passes room for three floats. */
+ * rows whose neighbour vote needed exact re-measurement, stats[3] = rows whose candidate buffer overflowed and that were
+ * settled by the second (listing) tensor-core pass.  The caller passes room for four floats. */
 int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max_rank_error, void *stream);
 
 /* Tuning / path selection for experiments and tests.  Options: "hist_stride_k4" (1 | 2), "hist_contigs_per_item",
+ * "score_list_pass" (0 = overflowed rows skip the listing pass and go to the exhaustive kernels),
  * "score_path" (0 = tensor cores when the shape allows, 1 = exhaustive float64 only, 2 = tensor cores or error),
  * "score_stats" (1 = collect error-interval diagnostics, slower), "time_kernels" (1 = bracket the hot kernels with CUDA
  * events for phm_last_kernel_ms). */

@@ -39,6 +39,7 @@ extern int hist_stride_for_k4;
 extern int hist_contigs_per_item;
 extern int score_path;
 extern int score_collect_stats;
+extern int score_list_pass;
 extern int score_debug;
 int kmer_hist_last_ms(float *ms);
 
@@ -78,6 +79,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "time_kernels")) { time_kernels = value != 0; return PHM_OK; }
     if (!strcmp(name, "score_debug")) { score_debug = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_stats")) { score_collect_stats = value != 0; return PHM_OK; }
+    if (!strcmp(name, "score_list_pass")) { score_list_pass = value != 0; return PHM_OK; }
     set_error("unknown option '%s'", name);
     return PHM_E_ARG;
 }

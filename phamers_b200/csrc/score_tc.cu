@@ -45,6 +45,7 @@ namespace phm {
 
 int score_debug = 0;              // option "score_debug": timing experiments only (1 = epilogue skips the scan, 2 = scan without hits)
 int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record how much of the bound is used
+int score_list_pass = 1;          // option "score_list_pass": 0 = overflowed rows go straight to the exhaustive kernels
 
 namespace tc {
 
@@ -67,6 +68,10 @@ constexpr int NTHREADS = 64 + NEPI;
 constexpr int TMEM_COLS = 512;            // two sets of (2 halves x 128 columns) FP32 accumulators
 constexpr float SCALE = (float)PREP_SCALE;  // operands are scaled by 2^12 -> accumulator = 2^24 a'.b'
 static_assert(KDIM == PREP_DIM, "score_common.cuh prepares 256-wide rows");
+constexpr int LIST_MAX_ROWS = 16384;      // rows the second ("list") tensor-core pass can take (multiple of MT)
+constexpr int64_t LIST_POOL = (int64_t)1 << 25;   // listed references of all such rows together (4 bytes each); rows that do not fit go to the exhaustive kernels
+constexpr uint32_t LIST_NO_ROOM = 0xFFFFFFFFu;
+static_assert(LIST_MAX_ROWS % MT == 0, "whole contig tiles");
 constexpr double NORM_SCALE = 8388608.0;  // 2^23: ranking value = 2^23 (|b'|^2 - 2 a'.b')
 constexpr float PAD_NORM = 3.0e38f;
 constexpr double EPS_ACC = 1.0 / 65536.0; // FP32 accumulation allowance relative to |A| |B|
@@ -329,6 +334,63 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
     scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
 }
 
+// ---------------- list mode: second pass over the rows whose candidate buffer overflowed ----------------
+// After the first pass such a row has a FINAL threshold T (the k-th smallest upper bound among what it kept), so no running
+// state is needed: every reference with lo_j <= T is appended to the row's list in global memory, independently per
+// reference tile -- which lets (contig tile, reference slice) pairs run on different CTAs.  score_list_decide_kernel then
+// measures the listed references exactly.  The pass runs twice: first it only COUNTS the references under each threshold, a
+// prefix sum (tc_list_scan_kernel) gives every row its range in one shared pool, then the same pass FILLS the ranges
+// (cols != nullptr).  Lists are usually short (the interval is ~1 % of the distance) but a contig far from every reference
+// can have thousands of references inside it; only rows that do not fit in the pool go to the exhaustive kernels.
+__device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c, int n_class, float C,
+                                           float T, uint32_t *cnt, uint32_t *cols) {
+    float lo[32], gm[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const uint4 nb = lds_v4(nbs_c + 16u * g);
+        const uint4 pp = lds_v4(p_c + 16u * g);
+        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]));
+        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]));
+        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]));
+        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]));
+        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
+    }
+    const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+    if (!__any_sync(FULL, m <= T)) return;
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hits |= (lo[j] <= T ? 1u : 0u) << j;
+    const int real = n_class - col_c;                    // columns of this chunk that are references (the rest is padding)
+    if (real < 32) hits &= real <= 0 ? 0u : ((1u << real) - 1u);
+    while (hits) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1u;
+        const uint32_t pos = atomicAdd(cnt, 1u);
+        if (cols) cols[pos] = (uint32_t)(col_c + j);
+    }
+}
+
+__device__ __forceinline__ void list_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float T,
+                                          uint32_t *cnt, uint32_t *cols) {
+    uint32_t ra[32], rb[32];
+    __syncwarp();
+    tmem_ld32_issue(taddr, ra);
+    tmem_wait_ld();
+    tmem_ld32_issue(taddr + 32u, rb);
+    list_chunk(ra, nbs_addr, p_addr, col0, n_class, C, T, cnt, cols);
+    __syncwarp();
+    tmem_wait_ld();
+    tmem_ld32_issue(taddr + 64u, ra);
+    list_chunk(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, T, cnt, cols);
+    __syncwarp();
+    tmem_wait_ld();
+    tmem_ld32_issue(taddr + 96u, rb);
+    list_chunk(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, T, cnt, cols);
+    __syncwarp();
+    tmem_wait_ld();
+    list_chunk(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, T, cnt, cols);
+}
+
 struct TcParams {
     int64_t n_points;
     int n_mtiles;
@@ -344,9 +406,32 @@ struct TcParams {
     int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
     uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 = centroid overflow)
     float2 *drop_lo;                     // [n_points] smallest lower bound of a dropped negative (.x) / positive (.y) reference
+    float *thr_out;                      // [n_points] the row's final threshold: k-th smallest upper bound over every reference seen, kept or dropped
+    // list mode (template flag LIST): map_a / crow describe the compacted rows, n_mtiles is derived from *list_count
+    const unsigned long long *list_count; int list_max_rows;
+    const float *list_thr;               // [list rows] final threshold of the row
+    uint32_t *list_cnt;                  // [list rows] references listed so far
+    const uint32_t *list_off;            // [list rows] start of the row's range in list_cols (fill pass), LIST_NO_ROOM = skip
+    uint32_t *list_cols;                 // pool of listed columns; nullptr = counting pass
 };
 
-template <int KN>
+// Work items of one CTA: contig tiles (first pass) or (contig tile, reference slice) pairs (list pass); every role of the CTA
+// walks the same sequence.
+struct TcSchedule { int n_items, n_slices; long long n_rows; };
+template <bool LIST>
+__device__ __forceinline__ TcSchedule tc_schedule(const TcParams &p) {
+    TcSchedule s;
+    if (!LIST) { s.n_items = p.n_mtiles; s.n_slices = 1; s.n_rows = p.n_points; return s; }
+    unsigned long long cnt = *p.list_count;
+    if (cnt > (unsigned long long)p.list_max_rows) cnt = (unsigned long long)p.list_max_rows;
+    const int n_mt = (int)((cnt + MT - 1) / MT);
+    int slices = n_mt ? (int)gridDim.x / n_mt : 1;
+    slices = slices < 1 ? 1 : (slices > p.nt_ref ? p.nt_ref : slices);
+    s.n_items = n_mt * slices; s.n_slices = slices; s.n_rows = (long long)cnt;
+    return s;
+}
+
+template <int KN, bool LIST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -387,19 +472,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(generic_x + (tmem_slot - sm_x));
+    const TcSchedule sched = tc_schedule<LIST>(p);
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t bstage = 0, bphase = 0, tile = 0;
             int it = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x, ++it) {
+                const int mt = item / sched.n_slices, sl = item - mt * sched.n_slices;
+                const int nt_lo = LIST ? (int)((long long)p.nt_ref * sl / sched.n_slices) : 0;
+                const int nt_hi = LIST ? (int)((long long)p.nt_ref * (sl + 1) / sched.n_slices) : nt_total;
                 mbar_wait(bar_a_empty, (uint32_t)((it & 1) ^ 1));
                 mbar_expect_tx(bar_a_full, A_BYTES);
                 for (int h = 0; h < 2; ++h)
                     for (int kc = 0; kc < NKC; ++kc)
                         tma_load_2d(sm_a + (h * NKC + kc) * BLOCK_BYTES, &map_a, bar_a_full, kc * BK, mt * MT + h * BM);
-                for (int nt = 0; nt < nt_total; ++nt, ++tile) {
+                for (int nt = nt_lo; nt < nt_hi; ++nt, ++tile) {
                     for (int kc = 0; kc < NKC; ++kc) {
                         mbar_wait(bar_b_empty + 8 * bstage, bphase ^ 1u);
                         mbar_expect_tx(bar_b_full + 8 * bstage, BLOCK_BYTES);
@@ -425,9 +514,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
         const uint32_t a_lo = desc_lo | ((sm_a & 0x3FFFFu) >> 4), b_lo = desc_lo | ((sm_b & 0x3FFFFu) >> 4);
         uint32_t bstage = 0, bphase = 0, tile = 0;
         int it = 0;
-        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x, ++it) {
+            const int sl = item % sched.n_slices;
+            const int nt_lo = LIST ? (int)((long long)p.nt_ref * sl / sched.n_slices) : 0;
+            const int nt_hi = LIST ? (int)((long long)p.nt_ref * (sl + 1) / sched.n_slices) : nt_total;
             mbar_wait(bar_a_full, (uint32_t)(it & 1));
-            for (int nt = 0; nt < nt_total; ++nt, ++tile) {
+            for (int nt = nt_lo; nt < nt_hi; ++nt, ++tile) {
                 const uint32_t set = tile & 1u;
                 mbar_wait(bar_t_empty + 8 * set, ((tile >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -463,12 +555,37 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
         const int row_in_tile = half * BM + q * 32 + lane;
         const uint32_t cand_addr = sm_cand + 8u * (uint32_t)row_in_tile;
         uint32_t tile = 0;
-        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
+        for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
+            const int mt = item / sched.n_slices;
             const int64_t row = (int64_t)mt * MT + row_in_tile;
-            float C = (row < p.n_points && p.debug != 2) ? p.crow[row] : NAN;
+            float C = (row < sched.n_rows && p.debug != 2) ? p.crow[row] : NAN;
             const bool live = C >= 0.0f;                           // false for padding rows and NaN feature rows
             const float init = live ? INFINITY : -INFINITY;        // -inf: nothing ever qualifies
             if (!live) C = 0.0f;
+            if constexpr (LIST) {
+                const int sl = item - mt * sched.n_slices;
+                const int nt_lo = (int)((long long)p.nt_ref * sl / sched.n_slices), nt_hi = (int)((long long)p.nt_ref * (sl + 1) / sched.n_slices);
+                float T = live ? p.list_thr[row] : -INFINITY;
+                uint32_t *my_cnt = p.list_cnt + (live ? row : 0);
+                uint32_t *my_cols = nullptr;
+                if (p.list_cols && live) {
+                    const uint32_t off = p.list_off[row];
+                    if (off == LIST_NO_ROOM) T = -INFINITY;
+                    else my_cols = p.list_cols + off;
+                }
+                for (int nt = nt_lo; nt < nt_hi; ++nt, ++tile) {
+                    const uint32_t set = tile & 1u;
+                    const uint32_t stg = sm_stg + set * (2 * BN * 4);
+                    mbar_wait(bar_n_full + 8 * set, (tile >> 1) & 1u);
+                    mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
+                    list_tile(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, T, my_cnt, my_cols);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
+                }
+            } else {
             float ur[KN], up[1], un[1];
 #pragma unroll
             for (int i = 0; i < KN; ++i) ur[i] = init;
@@ -519,7 +636,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                 }
                 p.meta[row] = (uint32_t)cnt_r | ((uint32_t)cnt_p << 8) | ((uint32_t)cnt_n << 16) | (flags << 24);
                 p.drop_lo[row] = make_float2(drop_lo[0], drop_lo[1]);
+                p.thr_out[row] = ur[KN - 1];
             }
+            }   // first pass
         }
     }
 
@@ -626,12 +745,15 @@ struct DecideParams {
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
     const double *cnorm_points;        // centred squared norms of the query rows (NaN = NaN feature row)
-    const uint2 *cand; const float *cand_up; const uint32_t *meta; const float2 *drop_lo;
+    const uint2 *cand; const float *cand_up; const uint32_t *meta; const float2 *drop_lo; const float *thr;
     int k_neighbors;
     double *knn, *kmeans, *combo;
     int64_t *fallback_rows; unsigned long long *fallback_count;
     float *stats;                      // when non-null: [0] max |x - exact| / (C P) (must stay <= 1), [1] max |x - exact| in d2 units
     unsigned long long *rows_remeasured;
+    // rows with an overflowed buffer but a final threshold: handed to the list pass instead of the exhaustive kernels
+    int64_t *list_rows; unsigned long long *list_count; int list_max_rows;
+    float *list_thr; double *list_km;
 };
 
 __device__ __forceinline__ double warp_exact_d2(const double (&x)[KDIM / 32], const double *__restrict__ b, int lane) {
@@ -660,7 +782,8 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
     const int kn = p.k_neighbors;
     for (int64_t row = warp; row < p.n_points; row += n_warps) {
         const double na = p.cnorm_points[row];
-        bool fallback = false;
+        bool fallback = false, listable = false;
+        float list_thr = 0.f;
         double knn = NAN, km = NAN;
         if (!isnan(na)) {
             double x[KDIM / 32];
@@ -668,7 +791,12 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             const uint32_t meta = p.meta[row];
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
             const float2 dropped = p.drop_lo[row];                      // smallest lower bound of a dropped negative / positive reference
-            fallback = (meta >> 24) != 0u || cnt_r < kn;
+            const bool cent_overflow = (meta >> 24) != 0u;              // a centroid buffer overflowed: all centroids are measured below
+            // fewer kept candidates than k: the k smallest upper bounds belonged to candidates that were dropped when the buffer was
+            // full.  The kernel's own final threshold (over kept AND dropped candidates) is still valid, so the list pass can take the row.
+            fallback = cnt_r < kn;
+            listable = fallback;
+            list_thr = p.thr[row];
             uint2 ent = make_uint2(0u, 0u);
             float up_f = INFINITY;
             if (lane < NENT) { ent = p.cand[row * NENT + lane]; up_f = p.cand_up[row * NENT + lane]; }
@@ -703,7 +831,7 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
                     // can be read off
                     if (pos_mask == band && !lost_neg) knn = 1.0;
                     else if (pos_mask == 0u && !lost_pos) knn = -1.0;
-                    else fallback = true;
+                    else { fallback = true; listable = true; }
                 } else if (n_band == kn || pos_mask == 0u || pos_mask == band) {
                     // the k nearest are exactly the band, or every possible member votes the same way
                     const int pos = (pos_mask == band) ? kn : ((pos_mask == 0u) ? 0 : __popc(pos_mask));
@@ -754,10 +882,23 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
             // ---------------- nearest centroid of each class ----------------
             if (p.n_cent_pos > 0 && p.n_cent_neg > 0) {
                 double e2[2] = {INFINITY, INFINITY};
-                if (cnt_p < 1 || cnt_n < 1) fallback = true;
                 const double u_p = warp_min_d(is_pos ? upper : INFINITY), u_n = warp_min_d(is_neg ? upper : INFINITY);
                 unsigned rest_p = __ballot_sync(FULL, is_pos && lower <= u_p);
                 unsigned rest_n = __ballot_sync(FULL, is_neg && lower <= u_n);
+                if (cent_overflow || cnt_p < 1 || cnt_n < 1) {
+                    // more than CAP_C centroids of a class inside the interval of the nearest one (rare): every centroid, exactly
+                    rest_p = 0u; rest_n = 0u;
+                    for (int64_t c = 0; c < p.n_cent_pos; c += 2) {
+                        const int64_t c1 = c + 1 < p.n_cent_pos ? c + 1 : c;
+                        const double a0 = warp_exact_d2(x, p.cent_pos + c * KDIM, lane), a1 = warp_exact_d2(x, p.cent_pos + c1 * KDIM, lane);
+                        e2[0] = fmin(e2[0], fmin(a0, a1));
+                    }
+                    for (int64_t c = 0; c < p.n_cent_neg; c += 2) {
+                        const int64_t c1 = c + 1 < p.n_cent_neg ? c + 1 : c;
+                        const double a0 = warp_exact_d2(x, p.cent_neg + c * KDIM, lane), a1 = warp_exact_d2(x, p.cent_neg + c1 * KDIM, lane);
+                        e2[1] = fmin(e2[1], fmin(a0, a1));
+                    }
+                }
                 while (rest_p | rest_n) {                              // one candidate of each class per round: both rows in flight
                     const int sp = rest_p ? __ffs(rest_p) - 1 : 0, sn = rest_n ? __ffs(rest_n) - 1 : 0;
                     const int ip = __shfl_sync(FULL, my_idx, sp), in_ = __shfl_sync(FULL, my_idx, sn);
@@ -783,13 +924,177 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
         }
         if (lane == 0) {
             if (fallback) {
-                const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
-                p.fallback_rows[slot_out] = row;
+                bool listed = false;
+                if (listable && p.list_rows) {
+                    const unsigned long long slot = atomicAdd(p.list_count, 1ull);
+                    if (slot < (unsigned long long)p.list_max_rows) {
+                        p.list_rows[slot] = row; p.list_thr[slot] = list_thr; p.list_km[slot] = km;
+                        listed = true;
+                    }
+                }
+                if (!listed) {
+                    const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
+                    p.fallback_rows[slot_out] = row;
+                }
             } else {
                 if (p.knn) p.knn[row] = knn;
                 if (p.kmeans) p.kmeans[row] = km;
                 if (p.combo) p.combo[row] = knn + km;                   // scripts/phamer.py:313
             }
+        }
+    }
+}
+
+// ---------------- list pass: compaction of its rows, and the exact decision over the listed references ----------------
+__global__ void __launch_bounds__(256) tc_list_gather_kernel(const __half *__restrict__ a_op, const float *__restrict__ crow,
+                                                             const int64_t *__restrict__ list_rows, const unsigned long long *list_count,
+                                                             int max_rows, __half *__restrict__ a_list, float *__restrict__ crow_list,
+                                                             uint32_t *__restrict__ list_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long cnt = *list_count;
+    if (cnt > (unsigned long long)max_rows) cnt = (unsigned long long)max_rows;
+    const int64_t padded = (int64_t)((cnt + MT - 1) / MT) * MT;
+    for (int64_t slot = warp; slot < padded; slot += n_warps) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        float c = NAN;                                                 // padding rows of the last tile are not live
+        if (slot < (int64_t)cnt) {
+            const int64_t row = list_rows[slot];
+            v = reinterpret_cast<const uint4 *>(a_op)[row * (KDIM * 2 / 16) + lane];
+            c = crow[row];
+        }
+        reinterpret_cast<uint4 *>(a_list)[slot * (KDIM * 2 / 16) + lane] = v;
+        if (lane == 0) { crow_list[slot] = c; list_cnt[slot] = 0u; }
+    }
+}
+
+// exclusive prefix sum of the per-row counts -> ranges in the pool; counts are kept in list_n and cleared for the fill pass
+__global__ void __launch_bounds__(1024) tc_list_scan_kernel(const unsigned long long *list_count, int max_rows, uint32_t *list_cnt,
+                                                            uint32_t *list_n, uint32_t *list_off) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    unsigned long long cnt = *list_count;
+    if (cnt > (unsigned long long)max_rows) cnt = (unsigned long long)max_rows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0ull;
+    __syncthreads();
+    for (unsigned long long i0 = 0; i0 < cnt; i0 += 1024) {
+        const unsigned long long i = i0 + threadIdx.x;
+        const unsigned long long mine = i < cnt ? list_cnt[i] : 0u;
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(FULL, wi, o);
+                if (lane >= o) wi += up;
+            }
+            s_warp[lane] = wi - w;                                     // exclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long start = s_base + s_warp[warp] + incl - mine;
+        if (i < cnt) {
+            list_n[i] = (uint32_t)mine;
+            list_off[i] = (start + mine <= (unsigned long long)LIST_POOL) ? (uint32_t)start : LIST_NO_ROOM;
+            list_cnt[i] = 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = start + mine;
+        __syncthreads();
+    }
+}
+
+struct ListDecideParams {
+    const double *points; const uint32_t *point_counts;
+    const double *refs; int64_t n_refs; int64_t n_positive;
+    int64_t perm_a, perm_c;
+    const int64_t *list_rows; const unsigned long long *list_count; int list_max_rows;
+    const uint32_t *list_n; const uint32_t *list_off; const uint32_t *list_cols; const double *list_km;
+    int k_neighbors;
+    double *knn, *kmeans, *combo;
+    int64_t *fallback_rows; unsigned long long *fallback_count;
+    unsigned long long *rows_listed;       // statistics: rows settled here
+};
+
+constexpr int LD_K = 5;                    // k_neighbors <= 5 on the tensor-core path
+constexpr int LD_U = 4;                    // listed references in flight per warp
+
+// One warp per listed row: float64 direct-difference distance (the arithmetic of every other exact path) to each listed
+// reference, k smallest by (distance, reference index), vote.  The centroid part of the score was settled by score_decide_kernel.
+__global__ void __launch_bounds__(256) score_list_decide_kernel(ListDecideParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long cnt = *p.list_count;
+    if (cnt > (unsigned long long)p.list_max_rows) cnt = (unsigned long long)p.list_max_rows;
+    const int kn = p.k_neighbors;
+    for (int64_t slot = warp; slot < (int64_t)cnt; slot += n_warps) {
+        const int64_t row = p.list_rows[slot];
+        const uint32_t n = p.list_n[slot], off = p.list_off[slot];
+        if (off == LIST_NO_ROOM || n < (uint32_t)kn) {                 // no room in the pool: exhaustive kernels (n < kn cannot happen)
+            if (lane == 0) p.fallback_rows[atomicAdd(p.fallback_count, 1ull)] = row;
+            continue;
+        }
+        double x[KDIM / 32];
+        load_query_row(p.points, p.point_counts, row, lane, x);
+        double bd[LD_K];
+        int bi[LD_K];
+#pragma unroll
+        for (int i = 0; i < LD_K; ++i) { bd[i] = INFINITY; bi[i] = 0x7FFFFFFF; }
+        const uint32_t *cols = p.list_cols + off;
+        for (uint32_t c0 = 0; c0 < n; c0 += LD_U) {
+            double acc[LD_U];
+            int idx[LD_U];
+#pragma unroll
+            for (int t = 0; t < LD_U; ++t) {
+                const uint32_t c = c0 + t < n ? c0 + t : n - 1;
+                idx[t] = (int)((p.perm_a * (int64_t)cols[c] + p.perm_c) % p.n_refs);
+                const double *b = p.refs + (int64_t)idx[t] * KDIM;
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) {
+                    const double d = x[i] - b[lane + 32 * i];
+                    a = fma(d, d, a);
+                }
+                acc[t] = a;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int t = 0; t < LD_U; ++t) acc[t] += __shfl_xor_sync(FULL, acc[t], o);
+#pragma unroll
+            for (int t = 0; t < LD_U; ++t) {
+                if (c0 + t >= n) break;
+                const double d = acc[t];
+                const int id = idx[t];
+#pragma unroll
+                for (int i = LD_K - 1; i > 0; --i) {
+                    const bool shift = d < bd[i - 1] || (d == bd[i - 1] && id < bi[i - 1]);
+                    const bool here = d < bd[i] || (d == bd[i] && id < bi[i]);
+                    bi[i] = shift ? bi[i - 1] : (here ? id : bi[i]);
+                    bd[i] = shift ? bd[i - 1] : (here ? d : bd[i]);
+                }
+                if (d < bd[0] || (d == bd[0] && id < bi[0])) { bd[0] = d; bi[0] = id; }
+            }
+        }
+        if (lane == 0) {
+            int pos = 0;
+#pragma unroll
+            for (int t = 0; t < LD_K; ++t) pos += (t < kn && (int64_t)bi[t] < p.n_positive);
+            const double knn = (2 * pos > kn) ? 1.0 : -1.0;               // scripts/learning.py:128
+            const double km = p.list_km[slot];
+            if (p.knn) p.knn[row] = knn;
+            if (p.kmeans) p.kmeans[row] = km;
+            if (p.combo) p.combo[row] = knn + km;                       // scripts/phamer.py:313
+            atomicAdd(p.rows_listed, 1ull);
         }
     }
 }
@@ -1102,10 +1407,13 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct TcWorkspace {
-    unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 256-byte header
+    unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 512-byte header
+    unsigned long long *list_count, *rows_listed;
+    int list_max_rows;
+    int64_t *list_rows; float *list_thr; double *list_km; float *list_crow; uint32_t *list_cnt, *list_n, *list_off, *list_cols; __half *a_list;
     __half *a_op, *b_op;
     float *nbs, *pnorm, *crow;
-    uint2 *cand; float *cand_up; uint32_t *meta; float2 *drop_lo;
+    uint2 *cand; float *cand_up; uint32_t *meta; float2 *drop_lo; float *thr_out;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
     double *cnorm_points;
     int64_t *fallback_rows;
@@ -1118,7 +1426,9 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     size_t off = 0;
     unsigned char *base = static_cast<unsigned char *>(ws);
     auto take = [&](size_t bytes) { unsigned char *p = base ? base + off : nullptr; off += align256(bytes); return p; };
-    unsigned char *head = take(256);
+    unsigned char *head = take(512);
+    w.list_count = reinterpret_cast<unsigned long long *>(head + 256);
+    w.rows_listed = reinterpret_cast<unsigned long long *>(head + 320);
     w.fallback_count = reinterpret_cast<unsigned long long *>(head);
     w.stats = reinterpret_cast<float *>(head + 64);
     w.rows_remeasured = reinterpret_cast<unsigned long long *>(head + 128);
@@ -1132,6 +1442,7 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.cand_up = reinterpret_cast<float *>(take((size_t)n * NENT * 4));
     w.meta = reinterpret_cast<uint32_t *>(take((size_t)n * 4));
     w.drop_lo = reinterpret_cast<float2 *>(take((size_t)n * 8));
+    w.thr_out = reinterpret_cast<float *>(take((size_t)n * 4));
     w.norm_points = reinterpret_cast<double *>(take((size_t)n * 8));
     w.norm_refs = reinterpret_cast<double *>(take((size_t)n_refs * 8));
     w.norm_cpos = reinterpret_cast<double *>(take((size_t)n_cp * 8));
@@ -1140,6 +1451,17 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.fallback_rows = reinterpret_cast<int64_t *>(take((size_t)n * 8));
     w.fb_parts = reinterpret_cast<FallbackPart *>(take(sizeof(FallbackPart) * FB_GRID * FB_SLICES));
     w.fb_tickets = reinterpret_cast<unsigned int *>(take(sizeof(unsigned int) * FB_GRID));
+    const int64_t lmax = round_up(n, MT) < LIST_MAX_ROWS ? round_up(n, MT) : LIST_MAX_ROWS;
+    w.list_max_rows = (int)lmax;
+    w.list_rows = reinterpret_cast<int64_t *>(take((size_t)lmax * 8));
+    w.list_thr = reinterpret_cast<float *>(take((size_t)lmax * 4));
+    w.list_km = reinterpret_cast<double *>(take((size_t)lmax * 8));
+    w.list_crow = reinterpret_cast<float *>(take((size_t)lmax * 4));
+    w.list_cnt = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
+    w.list_n = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
+    w.list_off = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
+    w.list_cols = reinterpret_cast<uint32_t *>(take((size_t)(lmax * 2048 < LIST_POOL ? lmax * 2048 : LIST_POOL) * 4));
+    w.a_list = reinterpret_cast<__half *>(take((size_t)lmax * KDIM * 2));
     w.bytes = off;
     return w;
 }
@@ -1167,8 +1489,17 @@ static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_
 static EventRing g_tc_ring;      // brackets of the score_tc_kernel launches (option "time_kernels")
 
 template <int KN>
+static int launch_tc_list(const CUtensorMap &map_list, const TcParams &p, cudaStream_t st) {
+    auto kern = score_tc_kernel<KN, true>;
+    PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kern<<<sm_count(), NTHREADS, SMEM_BYTES, st>>>(map_list, p);       // persistent; the number of rows is read on the device
+    PHM_CUDA_CHECK(cudaGetLastError());
+    return PHM_OK;
+}
+
+template <int KN>
 static int launch_tc(const CUtensorMap &map_a, const TcParams &p, cudaStream_t st) {
-    auto kern = score_tc_kernel<KN>;
+    auto kern = score_tc_kernel<KN, false>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int grid = sm_count();
     if (grid > p.n_mtiles) grid = p.n_mtiles;
@@ -1201,7 +1532,7 @@ int score_tc_begin(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t s
     if (ws_bytes < w.bytes) { set_error("workspace too small: %zu < %zu", ws_bytes, w.bytes); return PHM_E_WORKSPACE; }
     PHM_REQUIRE(n < ((int64_t)1 << 31) - MT && r_pad < ((int64_t)1 << 31), "problem too large for 32-bit TMA coordinates");
 
-    PHM_CUDA_CHECK(cudaMemsetAsync(w.fallback_count, 0, 256, st));
+    PHM_CUDA_CHECK(cudaMemsetAsync(w.fallback_count, 0, 512, st));
     int rc;
     int64_t perm_a, perm_c;
     ref_permutation(a.n_refs, &perm_a, &perm_c);
@@ -1217,7 +1548,7 @@ int score_tc_begin(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t s
 int score_tc(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t st, int *kernels_launched) {
     int rc = score_tc_begin(a, ws, ws_bytes, st, nullptr);
     if (rc != PHM_OK) return rc;
-    if (kernels_launched) *kernels_launched = 7;
+    if (kernels_launched) *kernels_launched = 12;
     return score_tc_finish(a, ws, ws_bytes, st, false);
 }
 
@@ -1242,9 +1573,11 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
-    p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo;
+    p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo; p.thr_out = w.thr_out;
     p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
     p.debug = score_debug;
+    p.list_count = w.list_count; p.list_max_rows = w.list_max_rows; p.list_thr = w.list_thr; p.list_cnt = w.list_cnt;
+    p.list_off = w.list_off; p.list_cols = nullptr;
     switch (a.k_neighbors) {
         case 1: rc = launch_tc<1>(map_a, p, st); break;
         case 3: rc = launch_tc<3>(map_a, p, st); break;
@@ -1258,16 +1591,55 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
-    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta; r.drop_lo = w.drop_lo;
+    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta; r.drop_lo = w.drop_lo; r.thr = w.thr_out;
     r.k_neighbors = a.k_neighbors;
     r.knn = a.knn; r.kmeans = a.kmeans; r.combo = a.combo;
     r.fallback_rows = w.fallback_rows; r.fallback_count = w.fallback_count;
     r.stats = score_collect_stats ? w.stats : nullptr;
     r.rows_remeasured = w.rows_remeasured;
+    const bool use_list = score_list_pass != 0;
+    r.list_rows = use_list ? w.list_rows : nullptr; r.list_count = w.list_count; r.list_max_rows = w.list_max_rows;
+    r.list_thr = w.list_thr; r.list_km = w.list_km;
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     score_decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
     PHM_CUDA_CHECK(cudaGetLastError());
+
+    // rows whose candidate buffer overflowed but whose threshold is final: second tensor-core pass that lists every reference
+    // under the threshold, then the exact decision over the lists (row count read on the device: no host synchronisation)
+    if (use_list) {
+        tc_list_gather_kernel<<<sm_count(), 256, 0, st>>>(w.a_op, w.crow, w.list_rows, w.list_count, w.list_max_rows, w.a_list, w.list_crow, w.list_cnt);
+        PHM_CUDA_CHECK(cudaGetLastError());
+        CUtensorMap map_list;
+        if ((rc = make_map(&map_list, w.a_list, w.list_max_rows)) != PHM_OK) return rc;
+        TcParams pl = p;
+        pl.crow = w.list_crow;
+        for (int pass = 0; pass < 2; ++pass) {                           // count, prefix sum, fill
+            pl.list_cols = pass ? w.list_cols : nullptr;
+            switch (a.k_neighbors) {
+                case 1: rc = launch_tc_list<1>(map_list, pl, st); break;
+                case 3: rc = launch_tc_list<3>(map_list, pl, st); break;
+                default: rc = launch_tc_list<5>(map_list, pl, st); break;
+            }
+            if (rc != PHM_OK) return rc;
+            if (pass == 0) {
+                tc_list_scan_kernel<<<1, 1024, 0, st>>>(w.list_count, w.list_max_rows, w.list_cnt, w.list_n, w.list_off);
+                PHM_CUDA_CHECK(cudaGetLastError());
+            }
+        }
+        ListDecideParams ld;
+        ld.points = a.points; ld.point_counts = a.point_counts;
+        ld.refs = a.refs; ld.n_refs = a.n_refs; ld.n_positive = a.n_positive;
+        ld.perm_a = perm_a; ld.perm_c = perm_c;
+        ld.list_rows = w.list_rows; ld.list_count = w.list_count; ld.list_max_rows = w.list_max_rows;
+        ld.list_n = w.list_n; ld.list_off = w.list_off; ld.list_cols = w.list_cols; ld.list_km = w.list_km;
+        ld.k_neighbors = a.k_neighbors;
+        ld.knn = a.knn; ld.kmeans = a.kmeans; ld.combo = a.combo;
+        ld.fallback_rows = w.fallback_rows; ld.fallback_count = w.fallback_count;
+        ld.rows_listed = w.rows_listed;
+        score_list_decide_kernel<<<sm_count() * 2, 256, 0, st>>>(ld);
+        PHM_CUDA_CHECK(cudaGetLastError());
+    }
 
     // rows whose candidate buffer overflowed: exhaustive float64, count read on the device
     FallbackParams f;
@@ -1289,14 +1661,17 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
 
 // statistics of the last score_tc call on this workspace
 int score_tc_stats(const void *ws, unsigned long long *fallback_rows, float *out3, cudaStream_t st) {
-    unsigned char host[256];
-    PHM_CUDA_CHECK(cudaMemcpyAsync(host, ws, 256, cudaMemcpyDeviceToHost, st));
+    unsigned char host[512];
+    PHM_CUDA_CHECK(cudaMemcpyAsync(host, ws, 512, cudaMemcpyDeviceToHost, st));
     PHM_CUDA_CHECK(cudaStreamSynchronize(st));
     memcpy(fallback_rows, host, 8);
     memcpy(out3, host + 64, 8);                // [0] bound usage (<= 1 proves the interval), [1] largest ranking error in d2 units
     unsigned long long remeasured = 0;
     memcpy(&remeasured, host + 128, 8);
     out3[2] = (float)remeasured;               // rows whose neighbour vote needed exact re-measurement
+    unsigned long long listed = 0;
+    memcpy(&listed, host + 320, 8);
+    out3[3] = (float)listed;                   // rows settled by the list pass
     return PHM_OK;
 }
 

@@ -143,7 +143,7 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=
         # both paths: 4 row-preparation kernels (when non-empty) + scorer; the tensor-core path adds re-rank + exact fallback
         tc_path = (dim == 256 and k_neighbors in (1, 3, 5) and refs.shape[0] >= k_neighbors and cent_pos.shape[0]
                    and cent_neg.shape[0] and score_path_option != 1)
-        _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (3 if tc_path else 1))
+        _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (8 if tc_path else 1))
     return knn, kmeans, combo
 
 
@@ -163,7 +163,7 @@ def count_score_cuda(seq, offsets, refs, n_positive, cent_pos, cent_neg, k_neigh
                               ptr(cent_neg), cent_neg.shape[0], int(k_neighbors), ptr(counts), ptr(knn), ptr(kmeans), ptr(combo),
                               ptr(ws), ws.numel(), stream_ptr()))
     if n:
-        _launched(3 + 1 + 3)          # 3 reference preparations, histogram (+ operands), contraction, decision, fallback
+        _launched(3 + 1 + 8)          # 3 reference preparations, histogram (+ operands), contraction, decision, list pass (5), fallback (2)
     return counts, knn, kmeans, combo
 
 
@@ -186,10 +186,10 @@ def score_stats():
     if _last_score_ws[0] == "count_score":           # the scorer's share starts after the (256-byte aligned) count workspace
         skip = (lib.phm_kmer_count_workspace_bytes(0, 0, 4, 0) + 255) // 256 * 256
         ws = ws[skip:]
-    rows, err = ctypes.c_uint64(0), (ctypes.c_float * 3)()
+    rows, err = ctypes.c_uint64(0), (ctypes.c_float * 4)()
     check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
     return {"fallback_rows": int(rows.value), "max_bound_usage": float(err[0]), "max_rank_error": float(err[1]),
-            "rows_remeasured": int(err[2])}
+            "rows_remeasured": int(err[2]), "rows_listed": int(err[3])}
 
 
 def synth_contigs(seed, first_contig, n_contigs):

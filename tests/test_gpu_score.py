@@ -239,10 +239,17 @@ def test_fallback_kernels_match_exact_path(scoring, n_rows):
     cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
     try:
         _lib.set_option("score_debug", 1)
+        _lib.set_option("score_list_pass", 0)                            # otherwise the list pass would take these rows (see below)
         f_knn, f_km, f_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
         assert ops.score_stats()["fallback_rows"] == n_rows - 1          # the NaN row never asks for a fallback
+        # same rows through the list pass: no candidate kept means an infinite threshold, i.e. every reference is listed
+        _lib.set_option("score_list_pass", 1)
+        l_knn, l_km, l_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
+        st = ops.score_stats()
+        assert st["rows_listed"] == n_rows - 1 and st["fallback_rows"] == 0
     finally:
         _lib.set_option("score_debug", 0)
+        _lib.set_option("score_list_pass", 1)
     t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
     try:
         ops.set_score_path("exact")
@@ -251,6 +258,60 @@ def test_fallback_kernels_match_exact_path(scoring, n_rows):
         ops.set_score_path("auto")
     ok = ~np.isnan(e_combo)
     assert ok.sum() == n_rows - 1 and np.isnan(f_combo[-1]) and np.isnan(t_combo[-1])
-    assert np.array_equal(f_knn[ok], e_knn[ok]) and np.array_equal(t_knn[ok], e_knn[ok])
+    assert np.array_equal(f_knn[ok], e_knn[ok]) and np.array_equal(t_knn[ok], e_knn[ok]) and np.array_equal(l_knn[ok], e_knn[ok])
+    assert np.array_equal(l_combo[ok], f_combo[ok])
     assert np.max(np.abs(f_km[ok] - e_km[ok])) <= 1e-12
     assert np.array_equal(f_km[ok], t_km[ok])                            # centroid term: same arithmetic on every path
+
+
+def test_list_pass_settles_overflowed_rows(scoring):
+    """Reference sets that are clouds of near-identical rows with MIXED labels overflow the 10-slot candidate buffers of the
+    first tensor-core pass.  Such rows have a final threshold, so a second pass lists every reference under it (count, prefix
+    sum, fill: lists of any length share one pool -- the 2000-row cloud gives lists far longer than the others) and the exact
+    decision is taken over the list (rows_listed).  With the list pass switched off the same rows take the exhaustive kernels.
+    Every road must give the exhaustive float64 scorer's votes and scores."""
+    import torch
+    from phamers_b200 import _lib, kmer, ops, references
+    g, pos, neg = scoring
+    rng = np.random.default_rng(42)
+    _, pos_c, _, neg_c = references.load_reference_counts()
+    both = np.vstack((pos_c, neg_c)).astype(np.float64)
+    src_a = both[rng.choice(both.shape[0], size=40, replace=False)]
+    src_b = both[int(rng.integers(0, both.shape[0]))]
+    # row totals differ from row to row: with one common total the distances are quantised and tie exactly at the k-th place
+    cloud_a = [rng.multinomial(int(rng.integers(15000, 25000)), s / s.sum()) for s in src_a for _ in range(250)]
+    cloud_b = [rng.multinomial(int(rng.integers(40000000, 60000000)), src_b / src_b.sum()) for _ in range(2000)]
+    ref_counts = np.stack(cloud_a + cloud_b).astype(np.int64)
+    ref_counts = ref_counts[rng.permutation(len(ref_counts))]             # labels (first half positive) mixed inside every cloud
+    refs = torch.from_numpy(kmer.normalize_counts(ref_counts)).cuda()
+    n_pos = len(ref_counts) // 2
+    queries = [rng.multinomial(int(rng.integers(15000, 25000)), s / s.sum()) for s in src_a for _ in range(15)]
+    queries += [rng.multinomial(int(rng.integers(40000000, 60000000)), src_b / src_b.sum()) for _ in range(50)]
+    queries += list(g["query_counts"])
+    counts = torch.from_numpy(np.stack(queries).astype(np.int32)).cuda()
+    cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
+    cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
+    try:
+        ops.set_score_path("tc")
+        t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, 3)]
+        stats = ops.score_stats()
+        k5 = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, 5)]
+        k1 = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, 1)]
+        _lib.set_option("score_list_pass", 0)
+        n_knn, n_km, n_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, 3)]
+        stats_off = ops.score_stats()
+        ops.set_score_path("exact")
+        e_knn, e_km, e_combo = [t.cpu().numpy() for t in ops.score_cuda(ops.normalize_cuda(counts), refs, n_pos, cp, cn, 3)]
+        e5 = [t.cpu().numpy() for t in ops.score_cuda(ops.normalize_cuda(counts), refs, n_pos, cp, cn, 5)]
+        e1 = [t.cpu().numpy() for t in ops.score_cuda(ops.normalize_cuda(counts), refs, n_pos, cp, cn, 1)]
+    finally:
+        _lib.set_option("score_list_pass", 1)
+        ops.set_score_path("auto")
+    print("list pass on: %s   off: %s" % (stats, stats_off))
+    assert stats["rows_listed"] >= 50 and stats_off["rows_listed"] == 0
+    assert stats["fallback_rows"] == 0
+    assert stats["rows_listed"] + stats["fallback_rows"] == stats_off["fallback_rows"]
+    assert np.array_equal(t_knn, e_knn) and np.array_equal(n_knn, e_knn)
+    assert np.array_equal(k5[0], e5[0]) and np.array_equal(k1[0], e1[0])
+    assert np.max(np.abs(t_combo - e_combo)) <= 1e-12 and np.max(np.abs(n_combo - e_combo)) <= 1e-12
+    assert np.array_equal(t_km, n_km)
