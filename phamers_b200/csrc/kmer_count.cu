@@ -40,6 +40,7 @@ struct HistCfg {
     static constexpr int DIRECT_BYTES = (STRIDE > 1) ? OUT_BINS * 4 : 0;
     static constexpr int ALIGN = TAB_BYTES < 16 ? 16 : TAB_BYTES;
     static constexpr int WARP_BYTES = ALIGN + DIRECT_BYTES;
+    static constexpr int PRE = TAB_BYTES >= 16384 ? 5 : 2;   // streaming loads in flight per lane
 };
 
 // --------------------------------------------------------------------------------------------------
@@ -47,7 +48,25 @@ struct HistCfg {
 // --------------------------------------------------------------------------------------------------
 // EMIT (k = 4, not canonical): the epilogue also writes the tensor-core scorer's query operands for the contig -- FP16 row, error
 // constant, centred norm -- so that the scoring stage starts without a preparation pass over the counts (phm_count_score).
-template <int K, int STRIDE, int WARPS, bool EMIT>
+// SWZ (canonical output, k >= 5, STRIDE 1): bin y lives at word y ^ (y >> (2K - 5)), i.e. its top five index bits are xor-ed
+// into the bank bits.  The reverse-complement gather of the epilogue reads rc(y) for 32 consecutive y at once; rc puts the
+// LAST digits of y first, so without the swizzle those 32 reads differ only in their top bits and land in ONE bank (a 32-way
+// conflict on every output word, as many shared-memory wavefronts as the whole counting loop); with it both gathers are
+// conflict-free.  The canonical look-up table (compact bin -> representative) is staged in shared memory once per CTA and the
+// reverse complement is computed arithmetically.
+template <int K>
+__device__ __forceinline__ uint32_t swz_off(uint32_t off) {            // off = 4 * bin
+    constexpr int SH = 2 * K > 5 ? 2 * K - 5 : 0;
+    return off ^ ((off >> SH) & 0x7Cu);
+}
+template <int K>
+__device__ __forceinline__ uint32_t revcomp_fast(uint32_t y) {
+    uint32_t x = __brev(y) >> (32 - 2 * K);                            // digits reversed, the two bits of each digit swapped
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    return x ^ (0x55555555u & ((1u << (2 * K)) - 1u));                 // A<->T, G<->C: low bit of every digit
+}
+
+template <int K, int STRIDE, int WARPS, bool EMIT, bool SWZ>
 __global__ void __launch_bounds__(WARPS * 32)
 kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
                  uint32_t *__restrict__ counts, double *__restrict__ freq,
@@ -75,6 +94,17 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
     if (STRIDE > 1)
         for (int i = lane; i < Cfg::OUT_BINS / 4; i += 32) sts_v4_zero(direct + 16u * i);
     __syncwarp();
+    // canonical look-up table into whichever end of the allocation the alignment left free (one of them has >= ALIGN / 2 bytes)
+    uint32_t lut = 0u;
+    if (SWZ) {
+        const uint32_t raw0 = smem_u32(smem_raw);
+        const uint32_t slack = base - raw0;
+        const uint32_t tail0 = base + (uint32_t)WARPS * Cfg::WARP_BYTES;
+        lut = (slack >= (uint32_t)Cfg::ALIGN - slack) ? raw0 : tail0;
+        for (int j = threadIdx.x; j < out_bins; j += WARPS * 32)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(lut + 2u * j), "h"(canon_lut[j]) : "memory");
+        __syncthreads();
+    }
 
     for (;;) {
         unsigned long long item = 0;
@@ -106,20 +136,29 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                     return decode_chunk(raw, startrel - pos, endrel - pos);
                 };
 
-                uint4 raw = load(0);
-                Dec cur = decode(raw, 0);
-                raw = load(1);
+                // PRE 128-bit loads in flight per lane.  The big tables (k >= 5) leave room for few warps per SM, and then the bytes
+                // in flight per SM, not the issue rate, decide whether HBM latency is covered.
+                constexpr int PRE = Cfg::PRE;
+                Dec cur = decode(load(0), 0);
+                uint4 ring[PRE - 1];
+#pragma unroll
+                for (int j = 0; j < PRE - 1; ++j) ring[j] = load(1 + j);
+#pragma unroll(PRE - 1)
                 for (int it = 0; it < n_iter; ++it) {
-                    const Dec nxt = decode(raw, it + 1);
-                    raw = load(it + 2);
+                    const Dec nxt = decode(ring[0], it + 1);
+#pragma unroll
+                    for (int j = 0; j + 1 < PRE - 1; ++j) ring[j] = ring[j + 1];
+                    ring[PRE - 2] = load(it + PRE);
                     uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
                     const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
                     if (lane == 31) hi_s = wrap_s;
                     const bool dirty = (cur.blank != 0u) | ((lane == 0) & (nxt.blank != 0u));
                     if (!__any_sync(FULL, dirty)) {
 #pragma unroll
-                        for (int p = 0; p < 16; p += STRIDE)
-                            red_shared_inc(tab | window_offset<W>(cur.s, hi_s, p));
+                        for (int p = 0; p < 16; p += STRIDE) {
+                            const uint32_t woff = window_offset<W>(cur.s, hi_s, p);
+                            red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : woff));
+                        }
                     } else {
                         uint32_t hi_b = __shfl_down_sync(FULL, cur.blank, 1);
                         const uint32_t wrap_b = __shfl_sync(FULL, nxt.blank, 0);
@@ -129,7 +168,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                             const uint32_t bl = window_bits<W>(cur.blank, hi_b, p);
                             const uint32_t idx = window_bits<W>(cur.s, hi_s, p);
                             if (bl == 0u) {
-                                red_shared_inc(tab + 4u * idx);
+                                red_shared_inc(tab + (SWZ ? swz_off<K>(4u * idx) : 4u * idx));
                             } else if (STRIDE > 1) {
                                 // a partly blank window still holds up to STRIDE clean k-mers
 #pragma unroll
@@ -201,11 +240,22 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
             } else {
                 // reverse-complement fold as a gather over the compact output bins: bin j is represented by y = canon_lut[j]
                 // (y <= rc(y)) and collects its partner unless it is its own reverse complement; stores are contiguous in j
+#pragma unroll 4
                 for (int j = lane; j < out_bins; j += 32) {
-                    const uint32_t y = canon_lut[j];
-                    const uint32_t r = rc_lut[y];
-                    uint32_t v = lds_u32(vst + 4u * y);
-                    if (r != y) v += lds_u32(vst + 4u * r);
+                    uint32_t y, r, v;
+                    if (SWZ) {
+                        uint16_t y16;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(y16) : "r"(lut + 2u * j) : "memory");
+                        y = y16;
+                        r = revcomp_fast<K>(y);
+                        v = lds_u32(vst + swz_off<K>(4u * y));
+                        if (r != y) v += lds_u32(vst + swz_off<K>(4u * r));
+                    } else {
+                        y = canon_lut[j];
+                        r = rc_lut[y];
+                        v = lds_u32(vst + 4u * y);
+                        if (r != y) v += lds_u32(vst + 4u * r);
+                    }
                     const int64_t o = c * (int64_t)out_bins + j;
                     if (counts) counts[o] = v;
                     if (freq) freq[o] = exact_quotient((double)v, dtotal, rtotal);
@@ -478,14 +528,17 @@ int kmer_hist_last_ms(float *ms) { return g_hist_ring.mean_ms(ms); }
 
 int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
 int hist_contigs_per_item = 4;
+int hist_stride_for_k5 = 1;          // 2 = k = 5 as 6-mers at every second base (4096-bin window table + 1024-bin direct table per warp): measured slower (10.1 vs 9.1 ms)
+int hist_warps_k6 = 13;
+int hist_canonical_swizzle = 1;      // k = 5, 6 canonical: bank-swizzled table + shared-memory look-up table (0 = plain layout, for comparison)
 
-template <int K, int STRIDE, int WARPS, bool EMIT = false>
+template <int K, int STRIDE, int WARPS, bool EMIT = false, bool SWZ = false>
 static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, double *freq,
                        const uint16_t *rc, const uint16_t *compact, int out_bins, unsigned long long *counter,
                        cudaStream_t st, tc::QueryEmit emit = tc::QueryEmit()) {
     using Cfg = HistCfg<K, STRIDE>;
     const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN;
-    auto kern = kmer_hist_kernel<K, STRIDE, WARPS, EMIT>;
+    auto kern = kmer_hist_kernel<K, STRIDE, WARPS, EMIT, SWZ>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -605,8 +658,18 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
             if (hist_stride_for_k4 == 2)
                 return launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
-        case 5: return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
-        case 6: return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 5:
+            if (hist_stride_for_k5 == 2)
+                return launch_hist<5, 2, 10>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            if (rc && hist_canonical_swizzle)
+                return launch_hist<5, 1, 8, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+        case 6:
+            if (hist_warps_k6 == 4)
+                return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            if (rc && hist_canonical_swizzle)
+                return launch_hist<6, 1, 13, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            return launch_hist<6, 1, 13>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
     }
     return PHM_E_ARG;
 }

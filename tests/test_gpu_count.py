@@ -225,3 +225,31 @@ def test_every_k4_window_stride_matches_oracle(stride):
             assert np.array_equal(_u32(canon), po.canonical_fold(want, 4))
     finally:
         _lib.set_option("hist_stride_k4", 2)
+
+
+@pytest.mark.parametrize("k,option,value,default", [(5, "hist_stride_k5", 1, 1), (5, "hist_stride_k5", 2, 1),
+                                                     (6, "hist_warps_k6", 4, 13), (6, "hist_warps_k6", 13, 13)])
+def test_k5_k6_kernel_variants_match_oracle(k, option, value, default):
+    """k = 5 as plain 5-mers or as 6-mers at every second base; k = 6 with 4 or 13 warps per CTA (deeper load pipeline)."""
+    from phamers_b200 import ops, _lib
+    rng = np.random.default_rng(1000 + 10 * k + value)
+    seq_a, off_a = _random_workload(rng, 1200, True)
+    lengths = np.array([17, 0, 1, 5, 6, 7, 16, 15, 31, 33, 0, 64, 1000, 7, 511, 513, 2, 300001, 100000, 9], dtype=np.int64)
+    off_c = np.concatenate(([0], np.cumsum(lengths)))
+    seq_c = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(off_c[-1]))
+    seq_c[off_c[17] + 150000] = ord("N")
+    seq_c[off_c[18]:off_c[19]] = ord("G")
+    _lib.set_option(option, value)
+    try:
+        for seq, off in ((seq_a, off_a), (seq_c, off_c)):
+            d_seq, d_off = _device(seq, off)
+            want = c_oracle.count(seq, off, k)
+            counts, freq = ops.count_cuda(d_seq, d_off, k, freq=True)
+            assert np.array_equal(_u32(counts), want)
+            assert np.array_equal(freq.cpu().numpy(), c_oracle.normalize(want), equal_nan=True)
+            canon, cfreq = ops.count_cuda(d_seq, d_off, k, canonical=True, freq=True)
+            want_c = po.canonical_fold(want, k)
+            assert np.array_equal(_u32(canon), want_c)
+            assert np.array_equal(cfreq.cpu().numpy(), c_oracle.normalize(want_c), equal_nan=True)
+    finally:
+        _lib.set_option(option, default)
