@@ -775,16 +775,27 @@ __device__ __forceinline__ double warp_min_d(double v) {
 }
 
 // One warp per contig; lane l < 16 holds candidate slot l (0..9 references, 10..12 positive centroids, 13..15 negative).
+// A warp takes 32 consecutive rows at a time: the cooperative part (gathers, reductions) row by row, then the scalar tail --
+// two square roots, a division and a float64 tanh, ~250 FP64 instructions that would otherwise be issued once per ROW with one
+// useful lane -- once per BATCH with lane = row, followed by coalesced stores.
 __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int kn = p.k_neighbors;
-    for (int64_t row = warp; row < p.n_points; row += n_warps) {
+    const bool has_cent = p.n_cent_pos > 0 && p.n_cent_neg > 0;
+    for (int64_t base = warp * 32; base < p.n_points; base += n_warps * 32) {
+    const int n_here = (int)(p.n_points - base < 32 ? p.n_points - base : 32);
+    double my_knn = NAN, my_e0 = INFINITY, my_e1 = INFINITY;
+    float my_thr = 0.f;
+    bool my_fallback = false, my_listable = false, my_live = false;
+    for (int rr = 0; rr < n_here; ++rr) {
+        const int64_t row = base + rr;
         const double na = p.cnorm_points[row];
         bool fallback = false, listable = false;
         float list_thr = 0.f;
-        double knn = NAN, km = NAN;
+        double knn = NAN;
+        double row_e0 = INFINITY, row_e1 = INFINITY;
         if (!isnan(na)) {
             double x[KDIM / 32];
             load_query_row(p.points, p.point_counts, row, lane, x);
@@ -880,7 +891,7 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
                 }
             }
             // ---------------- nearest centroid of each class ----------------
-            if (p.n_cent_pos > 0 && p.n_cent_neg > 0) {
+            if (has_cent) {
                 double e2[2] = {INFINITY, INFINITY};
                 const double u_p = warp_min_d(is_pos ? upper : INFINITY), u_n = warp_min_d(is_neg ? upper : INFINITY);
                 unsigned rest_p = __ballot_sync(FULL, is_pos && lower <= u_p);
@@ -918,30 +929,41 @@ __global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
                     rest_p &= rest_p - 1;
                     rest_n &= rest_n - 1;
                 }
-                const double e_pos = sqrt(e2[0]), e_neg = sqrt(e2[1]);
-                km = tanh((e_neg - e_pos) / (e_pos + e_neg));          // scripts/phamer.py:206-209
+                row_e0 = e2[0]; row_e1 = e2[1];
             }
         }
-        if (lane == 0) {
-            if (fallback) {
-                bool listed = false;
-                if (listable && p.list_rows) {
-                    const unsigned long long slot = atomicAdd(p.list_count, 1ull);
-                    if (slot < (unsigned long long)p.list_max_rows) {
-                        p.list_rows[slot] = row; p.list_thr[slot] = list_thr; p.list_km[slot] = km;
-                        listed = true;
-                    }
-                }
-                if (!listed) {
-                    const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
-                    p.fallback_rows[slot_out] = row;
-                }
-            } else {
-                if (p.knn) p.knn[row] = knn;
-                if (p.kmeans) p.kmeans[row] = km;
-                if (p.combo) p.combo[row] = knn + km;                   // scripts/phamer.py:313
-            }
+        if (lane == rr) {                                               // everything above is warp-uniform
+            my_knn = knn; my_e0 = row_e0; my_e1 = row_e1; my_thr = list_thr;
+            my_fallback = fallback; my_listable = listable; my_live = !isnan(na);
         }
+    }
+    // ---------------- scalar tail: lane = row ----------------
+    if (lane < n_here) {
+        const int64_t row = base + lane;
+        double km = NAN;
+        if (my_live && has_cent) {
+            const double e_pos = sqrt(my_e0), e_neg = sqrt(my_e1);
+            km = tanh((e_neg - e_pos) / (e_pos + e_neg));              // scripts/phamer.py:206-209
+        }
+        if (my_fallback) {
+            bool listed = false;
+            if (my_listable && p.list_rows) {
+                const unsigned long long slot = atomicAdd(p.list_count, 1ull);
+                if (slot < (unsigned long long)p.list_max_rows) {
+                    p.list_rows[slot] = row; p.list_thr[slot] = my_thr; p.list_km[slot] = km;
+                    listed = true;
+                }
+            }
+            if (!listed) {
+                const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
+                p.fallback_rows[slot_out] = row;
+            }
+        } else {
+            if (p.knn) p.knn[row] = my_knn;
+            if (p.kmeans) p.kmeans[row] = km;
+            if (p.combo) p.combo[row] = my_knn + km;                    // scripts/phamer.py:313
+        }
+    }
     }
 }
 
@@ -1600,7 +1622,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     const bool use_list = score_list_pass != 0;
     r.list_rows = use_list ? w.list_rows : nullptr; r.list_count = w.list_count; r.list_max_rows = w.list_max_rows;
     r.list_thr = w.list_thr; r.list_km = w.list_km;
-    int64_t blocks = (n + 7) / 8;
+    int64_t blocks = (n + 255) / 256;                                  // a warp takes 32 consecutive rows at a time
     if (blocks > 148 * 16) blocks = 148 * 16;
     score_decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
     PHM_CUDA_CHECK(cudaGetLastError());
