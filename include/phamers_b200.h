@@ -148,6 +148,25 @@ int phm_count_score(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_co
                     int k_neighbors, uint32_t *d_counts, double *d_knn, double *d_kmeans, double *d_combo,
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * FASTA ingest on the device (the caller / data-format row either side of the path).  Replaces the
+ * tokenisation kmer.count_file gets from Bio.SeqIO (scripts/kmer.py:131-139; scripts/fileIO.py:28-42): a record starts at a
+ * line beginning with '>', its sequence is every following line with '\n', '\r' and ' ' removed (k-mers span line breaks, never
+ * records), text before the first '>' is ignored.  Two calls, so that the caller can size the outputs in between:
+ *
+ *   phm_fasta_index    d_raw uint8[n_bytes] (16-byte aligned, allocation readable up to the next multiple of 16)
+ *                      -> d_result int64[4]: [0] records, [1] sequence bytes, [2] 1 if the file holds a tab / VT / FF (the reference
+ *                         strips those at line ends only: take the host path for such files), [3] internal
+ *   phm_fasta_extract  -> d_seq uint8[result[1]] sequence bytes end to end (ready for phm_kmer_count), d_offsets int64[records + 1],
+ *                         d_header_pos int64[records] byte position of each record's '>' in the file (the host reads the titles
+ *                         there); records beyond max_records are dropped
+ * Both use the same d_workspace (phm_fasta_workspace_bytes), which must stay untouched between them.
+ * ------------------------------------------------------------------------------------------- */
+size_t phm_fasta_workspace_bytes(int64_t n_bytes);
+int phm_fasta_index(const uint8_t *d_raw, int64_t n_bytes, int64_t *d_result, void *d_workspace, size_t workspace_bytes, void *stream);
+int phm_fasta_extract(const uint8_t *d_raw, int64_t n_bytes, const int64_t *d_result, uint8_t *d_seq, int64_t *d_offsets,
+                      int64_t *d_header_pos, int64_t max_records, const void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
  * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
  * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option

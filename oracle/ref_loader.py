@@ -157,3 +157,29 @@ def load_reference():
         m.logger.setLevel(logging.ERROR)
     _cache["mods"] = (kmer, learning, phamer)
     return _cache["mods"]
+
+
+def load_reference_cross_validate():
+    """The unmodified scripts/cross_validate.py, imported against the reference kmer / learning / phamer modules."""
+    if "cv" in _cache:
+        return _cache["cv"]
+    kmer, learning, phamer = load_reference()
+    d = reference_scripts_dir()
+    names = {"kmer": kmer, "learning": learning, "phamer": phamer}
+    saved = {name: sys.modules.get(name) for name in list(names) + ["cross_validate"]}
+    sys.modules.update(names)
+    sys.path.insert(0, d)
+    try:
+        sys.modules.pop("cross_validate", None)
+        cv = importlib.import_module("cross_validate")
+    finally:
+        sys.path.remove(d)
+        for name, mod in saved.items():
+            if mod is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = mod
+    import logging
+    cv.logger.setLevel(logging.ERROR)
+    _cache["cv"] = cv
+    return cv

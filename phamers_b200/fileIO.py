@@ -80,7 +80,10 @@ def split_fasta_bytes(raw):
         return [], np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
     # end of each header line (position of its '\n', or n)
     idx = np.searchsorted(newline, header_start)
-    header_end = np.where(idx < newline.shape[0], newline[np.minimum(idx, newline.shape[0] - 1)], n)
+    if newline.shape[0]:
+        header_end = np.where(idx < newline.shape[0], newline[np.minimum(idx, newline.shape[0] - 1)], n)
+    else:
+        header_end = np.full_like(header_start, n)                    # a lone header line without a line feed
     body_start = np.minimum(header_end + 1, n)
     body_end = np.concatenate((header_start[1:], [n]))
 
@@ -111,6 +114,37 @@ def split_fasta_bytes(raw):
     offsets = np.concatenate((kept_before[body_start], [kept_before[n]])).astype(np.int64)
     # bodies are disjoint and ordered, so offsets[i+1] == kept_before[body_end[i]]
     return ids, data[keep], offsets
+
+
+def read_fasta_arrays_cuda(fasta_file):
+    """Device-side tokenisation of a FASTA file (phm_fasta_index / phm_fasta_extract): the file's bytes go to the GPU once and
+    the sequence bytes never come back.  Returns (titles' first tokens, CUDA uint8 tensor of all sequence bytes end to end
+    [padded to 16], CUDA int64 offsets[n+1]).  Files holding a tab / VT / FF (stripped by the reference at line ends only) are
+    tokenised by the exact host path and uploaded.  Raises IOError when unreadable."""
+    import torch
+    from . import ops
+    raw = _open_bytes(fasta_file)
+    n = len(raw)
+    host = torch.empty((max((n + 15) // 16 * 16, 16),), dtype=torch.uint8, pin_memory=True)
+    if n:
+        host[:n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    if n == 0:
+        return [], torch.zeros((16,), dtype=torch.uint8, device="cuda"), torch.zeros((1,), dtype=torch.int64, device="cuda")
+    d_raw = host.to("cuda", non_blocking=True)                     # allocation padded to 16 bytes, as the scan requires
+    seq, offsets, header_pos, odd = ops.fasta_scan_cuda(d_raw[:n])
+    if odd:
+        ids, h_seq, h_off = split_fasta_bytes(raw)
+        total = int(h_off[-1])
+        pad = torch.zeros((max((total + 15) // 16 * 16, 16),), dtype=torch.uint8)
+        pad[:total] = torch.from_numpy(np.ascontiguousarray(h_seq[:total]).copy()) if total else pad[:0]
+        return ids, pad.cuda(), torch.from_numpy(np.ascontiguousarray(h_off)).cuda()
+    ids = []
+    for hs in header_pos.cpu().tolist():
+        he = raw.find(b"\n", hs)
+        title = raw[hs + 1:(he if he >= 0 else n)].decode("latin-1").rstrip()
+        tokens = title.split(None, 1)
+        ids.append(tokens[0] if tokens else "")
+    return ids, seq, offsets
 
 
 def read_fasta_arrays(fasta_file):

@@ -5,7 +5,7 @@ counting and normalising done by the CUDA kernels behind include/phamers_b200.h.
     reference (scripts/kmer.py)                  here
     count_string  :32      per-base Python loop  one phm_kmer_count launch
     count         :82      dispatch str / list   same dispatch, ONE launch for the whole list
-    count_file    :114     Bio.SeqIO + count     host FASTA split + one launch
+    count_file    :114     Bio.SeqIO + count     FASTA tokenised on the device (3 launches) + one launch
     count_directory :143   per-file sums         same
     normalize_counts :209  row / row-sum         phm_normalize_counts
     sequence_to_integers :183, get_kmer_index :199, kmers :224, extend_mers :235   plain host helpers
@@ -108,16 +108,34 @@ def count(data, kmer_length, symbols=DNA, normalize=False):
 def count_file(input_file, kmer_length, symbols=DNA, normalize=False):
     """scripts/kmer.py:114.  (ids ndarray[str], counts ndarray[n, bins]); (None, None) if the file cannot be read.
     Zipped files are ok."""
+    table = _translation(symbols)
+    bins = len(symbols) ** kmer_length
+    if table is None:
+        # usual case: the file's bytes go to the device once, records are found there (phm_fasta_index / _extract) and the
+        # sequence bytes feed the histogram kernel without ever coming back to the host
+        from . import ops, _lib
+        _lib.require_cuda()
+        try:
+            headers, d_seq, d_off = fileIO.read_fasta_arrays_cuda(input_file)
+        except IOError:
+            logger.warning("Could not read file: %s" % os.path.basename(input_file))
+            return None, None
+        ids = np.array([fileIO.get_id(h) for h in headers])
+        if len(ids) == 0:
+            return ids, np.zeros((0, bins), dtype=(float if normalize else int))
+        counts, freq = ops.count_cuda(d_seq, d_off, kmer_length, counts=not normalize, freq=normalize)
+        if normalize:
+            out = freq.cpu().numpy()
+            out[np.isnan(out).any(axis=1)] = 0.0                               # kmer.py:77: no division for empty rows
+            return ids, out
+        return ids, counts.cpu().numpy().view(np.uint32).astype(np.int64)
     try:
         headers, seq, offsets = fileIO.read_fasta_arrays(input_file)
     except IOError:
         logger.warning("Could not read file: %s" % os.path.basename(input_file))
         return None, None
     ids = np.array([fileIO.get_id(h) for h in headers])
-    table = _translation(symbols)
-    if table is not None:
-        seq = np.frombuffer(seq.tobytes().translate(table), dtype=np.uint8)
-    bins = len(symbols) ** kmer_length
+    seq = np.frombuffer(seq.tobytes().translate(table), dtype=np.uint8)
     if len(ids) == 0:
         return ids, np.zeros((0, bins), dtype=(float if normalize else int))
     return ids, count_arrays(seq, offsets, kmer_length, normalize=normalize)

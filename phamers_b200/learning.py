@@ -6,7 +6,9 @@ Drop-in for the hot-path part of the reference's scripts/learning.py.
                           equivalent is provided: there is no CPU arithmetic path in this package)
     get_centroids  :69, kmeans :131   reference-set preprocessing         -> host scikit-learn, see references.py
 
-The evaluation helpers of learning.py (dbscan, silhouettes, get_density, ROC metrics) are outside the hot path.
+    predictor_performance :185, get_truth_table :199, get_predictor_metrics :224   ROC and truth-table metrics (host)
+
+The other evaluation helpers of learning.py (dbscan, silhouettes, get_density) are outside the hot path.
 """
 import numpy as np
 
@@ -44,3 +46,41 @@ def kmeans(data, k, verbose=False, sort_by_size=False):
     if sort_by_size:
         raise NotImplementedError("sort_by_size is outside the hot path")
     return references.kmeans_assign(np.asarray(data), k)
+
+
+# ---- evaluation helpers used by cross_validate.py (host side: a handful of scalars per run) --------------------------
+def predictor_performance(positive_scores, negative_scores):
+    """scripts/learning.py:185-196: (false positive rate, true positive rate, ROC area under the curve)."""
+    from sklearn.metrics import auc, roc_curve
+    truth = np.append(np.ones(len(positive_scores)), np.zeros(len(negative_scores))).astype(bool)
+    predictions = np.append(positive_scores, negative_scores)
+    false_positive_rate, true_positive_rate, _ = roc_curve(truth, predictions)
+    return false_positive_rate, true_positive_rate, auc(false_positive_rate, true_positive_rate)
+
+
+def get_truth_table(positive_scores, negative_scores, threshold=0):
+    """scripts/learning.py:199-221: (TPR, FPR, FNR, TNR); a score >= threshold is a positive call."""
+    tp = np.sum(positive_scores >= threshold)
+    fp = np.sum(negative_scores >= threshold)
+    fn = np.sum(positive_scores < threshold)
+    tn = np.sum(negative_scores < threshold)
+    tpr = float(tp) / (tp + fn) if tp + fn != 0 else 0
+    fpr = float(fp) / (fp + tn) if fp + tn != 0 else 0
+    return tpr, fpr, 1 - tpr, 1 - fpr
+
+
+def get_predictor_metrics(positive_scores, negative_scores, threshold=0):
+    """scripts/learning.py:224-245: pandas Series tp fp fn tn tpr fpr fnr tnr ppv npv fdr acc."""
+    import pandas as pd
+    metrics = ["tp", "fp", "fn", "tn", "tpr", "fpr", "fnr", "tnr", "ppv", "npv", "fdr", "acc"]
+    series = pd.Series(index=metrics, dtype=float)
+    series["tp"] = np.sum(positive_scores >= threshold)
+    series["fp"] = np.sum(negative_scores >= threshold)
+    series["fn"] = np.sum(positive_scores < threshold)
+    series["tn"] = np.sum(negative_scores < threshold)
+    series["tpr"], series["fpr"], series["fnr"], series["tnr"] = get_truth_table(positive_scores, negative_scores, threshold=threshold)
+    series["ppv"] = float(series["tp"]) / (series["tp"] + series["fp"])
+    series["npv"] = float(series["tn"]) / (series["tn"] + series["fn"])
+    series["fdr"] = 1 - series["ppv"]
+    series["acc"] = float(series["tp"] + series["tn"]) / (series["tp"] + series["fp"] + series["fn"] + series["tn"])
+    return series

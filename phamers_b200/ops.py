@@ -192,6 +192,28 @@ def score_stats():
             "rows_remeasured": int(err[2]), "rows_listed": int(err[3])}
 
 
+def fasta_scan_cuda(raw):
+    """FASTA bytes on the device (contiguous CUDA uint8 tensor, 16-byte aligned) -> (seq uint8 [bases] end to end,
+    offsets int64 [records + 1], header_pos int64 [records], odd_whitespace bool).  `seq` is padded to a multiple of 16
+    bytes for phm_kmer_count.  One host synchronisation (the outputs are sized from the index pass).  When odd_whitespace is
+    True (tab / VT / FF in the file) the reference strips those bytes at line ends only: use the host tokeniser."""
+    lib = _lib.require_cuda()
+    raw = _as_u8_cuda(raw)
+    n = raw.numel()
+    ws_bytes = lib.phm_fasta_workspace_bytes(n)
+    ws = _workspace("fasta", ws_bytes)
+    result = torch.empty((4,), dtype=torch.int64, device="cuda")
+    check(lib.phm_fasta_index(ptr(raw), n, ptr(result), ptr(ws), ws_bytes, stream_ptr()))
+    n_records, n_kept, odd, _ = [int(v) for v in result.cpu().tolist()]
+    seq = torch.empty((max((n_kept + 15) // 16 * 16, 16),), dtype=torch.uint8, device="cuda")
+    offsets = torch.empty((n_records + 1,), dtype=torch.int64, device="cuda")
+    header_pos = torch.empty((max(n_records, 1),), dtype=torch.int64, device="cuda")
+    check(lib.phm_fasta_extract(ptr(raw), n, ptr(result), ptr(seq), ptr(offsets), ptr(header_pos), n_records, ptr(ws), ws_bytes,
+                                stream_ptr()))
+    _launched(3)
+    return seq, offsets, header_pos[:n_records], bool(odd)
+
+
 def synth_contigs(seed, first_contig, n_contigs):
     """Synthetic metagenome shard generated on the device.
     Returns (seq uint8[total], offsets int64[n+1])."""

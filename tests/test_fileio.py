@@ -38,6 +38,12 @@ def test_fasta_split_matches_reference_tokenisation(fasta, tmp_path):
     assert got == [s for _, s in po.parse_fasta_text(tricky)] == ["AT\tGCGG", "ACGT"]
     with pytest.raises(IOError):
         fileIO.read_fasta_arrays(str(tmp_path / "missing.fasta"))
+    # degenerate files
+    for raw in (b"", b"\n", b">", b">a", b">a\n", b"ACGT", b">a\nACGT", b"x\n>a b\n\nAC\n>\n>c\nG"):
+        ids, seq, off = fileIO.split_fasta_bytes(raw)
+        want = list(po.parse_fasta_text(raw.decode()))
+        assert ids == [(t.split(None, 1) or [""])[0] for t, _ in want]
+        assert [seq.tobytes().decode()[off[i]:off[i + 1]] for i in range(len(ids))] == [s for _, s in want]
     assert fileIO.split_fasta_bytes(b"") [0] == [] and fileIO.split_fasta_bytes(b"no header\nACGT\n")[0] == []
 
 
