@@ -30,6 +30,9 @@ class phamer_scorer(object):
         self.features_file = None
         self.fasta_file = None
         self.output_directory = None
+        self.data_directory = None
+        self.positive_features_file = None
+        self.negative_features_file = None
 
         self.data_ids = None
         self.data_points = None
@@ -82,7 +85,7 @@ class phamer_scorer(object):
             self.length_requirement = length_requirement
         ids, lengths = fileIO.get_fasta_lengths(self.fasta_file)
         long_ids = [ids[i] for i in range(len(ids)) if lengths[i] >= self.length_requirement]
-        self.data_points = self.data_points[np.in1d(self.data_ids, long_ids)]
+        self.data_points = self.data_points[np.isin(self.data_ids, long_ids)]
         self.data_ids = np.array(long_ids)
 
     def equalize_reference_data(self):
@@ -146,6 +149,29 @@ class phamer_scorer(object):
         finally:
             self.scoring_method = saved
 
+    # ---- files (scripts/phamer.py:405-436) -------------------------------------------------------------
+    def find_data_files(self):
+        """:406-415: default places of the reference feature tables inside a data directory."""
+        self.positive_features_file = os.path.join(self.data_directory, "reference_features", "positive_features.csv")
+        self.negative_features_file = os.path.join(self.data_directory, "reference_features", "negative_features.csv")
+
+    def find_input_files(self):
+        """:417-436: the single .fasta / .fa file of the input directory (a '*genes' file only as a last resort) and its single .csv."""
+        if self.input_directory and os.path.isdir(self.input_directory):
+            fasta_files = [f for f in os.listdir(self.input_directory) if f.endswith(".fasta") or f.endswith(".fa")]
+            if len(fasta_files) == 1:
+                self.fasta_file = os.path.join(self.input_directory, fasta_files[0])
+            elif fasta_files:
+                for potential_file in fasta_files:
+                    if not os.path.splitext(potential_file)[0].endswith("genes"):
+                        self.fasta_file = os.path.join(self.input_directory, potential_file)
+                        break
+                if self.fasta_file is None:
+                    self.fasta_file = os.path.join(self.input_directory, fasta_files[0])
+            features_files = [f for f in os.listdir(self.input_directory) if f.endswith(".csv")]
+            if len(features_files) == 1:
+                self.features_file = os.path.join(self.input_directory, features_files[0])
+
     # ---- outputs ----------------------------------------------------------------------------------------
     def get_phamer_output_filename(self):
         return os.path.join(self.output_directory, "phamer_scores.csv")              # :439-441
@@ -165,3 +191,65 @@ def score_points(scoring_data, positive_training_data, negative_training_data, m
     scorer.positive_data = positive_training_data
     scorer.negative_data = negative_training_data
     return scorer.score_points()
+
+
+def decide_files(scorer, args):
+    """scripts/phamer.py:470-507: explicit command-line files win over what the input / data directories hold; the output goes
+    to -out, else to <input directory>/phamer_output (the reference's misspelt `input_drectory` branch is dead code)."""
+    if args.kmer_length:
+        scorer.kmer_length = args.kmer_length
+    if args.input_directory:
+        scorer.input_directory = args.input_directory
+        scorer.find_input_files()
+    if args.data_directory:
+        scorer.data_directory = args.data_directory
+        scorer.find_data_files()
+    if args.output_directory:
+        scorer.output_directory = args.output_directory
+    else:
+        base = scorer.input_directory or os.path.dirname(args.fasta_file or args.features_file or "") or "."
+        scorer.output_directory = os.path.join(base, "phamer_output")
+    scorer.fasta_file = args.fasta_file or scorer.fasta_file
+    scorer.features_file = args.features_file or scorer.features_file
+    scorer.positive_features_file = args.positive_features or scorer.positive_features_file
+    scorer.negative_features_file = args.negative_features or scorer.negative_features_file
+
+
+def main(argv=None):
+    """The reference's command line (scripts/phamer.py:510-599) for the hot path: count the contigs of a FASTA (or read their
+    feature CSV), score them against the reference features, write <out>/phamer_scores.csv.  t-SNE and plots are out of scope."""
+    import argparse
+    parser = argparse.ArgumentParser(description="Scores contigs based on feature similarity (B200 path)",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("-in", "--input_directory", help="Directory containing input files")
+    parser.add_argument("-fasta", "--fasta_file", help="Fasta compilation file of unknown sequences")
+    parser.add_argument("-features", "--features_file", help="Input feature file")
+    parser.add_argument("-data", "--data_directory", help="Directory containing all relevant data files")
+    parser.add_argument("-pf", "--positive_features", help="positive feature file")
+    parser.add_argument("-nf", "--negative_features", help="negative feature file")
+    parser.add_argument("-out", "--output_directory", help="Directory to put output files")
+    parser.add_argument("-k", "--kmer_length", type=int, default=4, help="Length of k-mers analyzed")
+    parser.add_argument("-l", "--length_requirement", type=int, default=5000, help="Sequence length requirement")
+    parser.add_argument("-equal", "--equalize_reference", action="store_true", help="Use same number of reference data from each")
+    parser.add_argument("-m", "--method", default="combo", help="Learning algorithm name")
+    parser.add_argument("-do_tsne", "--do_tsne", action="store_true", help="(out of scope)")
+    parser.add_argument("-plot", "--plot_tsne", action="store_true", help="(out of scope)")
+    args = parser.parse_args(argv)
+    if args.do_tsne or args.plot_tsne:
+        raise NotImplementedError("t-SNE and plotting are outside the B200 hot path")
+    scorer = phamer_scorer()
+    decide_files(scorer, args)
+    scorer.scoring_method = args.method
+    scorer.load_reference_data(scorer.positive_features_file, scorer.negative_features_file)
+    scorer.load_data(length_requirement=args.length_requirement)
+    if args.equalize_reference:
+        scorer.equalize_reference_data()
+    if not os.path.isdir(scorer.output_directory):
+        os.makedirs(scorer.output_directory)
+    scorer.scores = scorer.score_points()
+    scorer.make_summary_file(args=args)
+    return scorer
+
+
+if __name__ == "__main__":
+    main()
