@@ -31,7 +31,7 @@ for _ in range(2):
     out = ops.fasta_scan_cuda(dev[:n])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 5
+reps = 20
 e0.record()
 for _ in range(reps):
     d_seq, d_off, d_hpos, odd = ops.fasta_scan_cuda(dev[:n])
