@@ -198,8 +198,12 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-        "config": {"workload": "synthetic metagenome 1M contigs, 1-100 kb lognormal, k=4 (configs[1]); bounded sample",
-                   "sample_contigs": n_sample, "sample_bases": bases},
+        # the same workload string as the B200 arm's default line; what is timed is a bounded sample of it
+        "config": {"workload": "synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=4 (BASELINE configs[1]), "
+                               "scored against %d shipped reference rows + %d centroids, method combo"
+                               % (args.contigs, 2 * n_ref, cents[0].shape[0] + cents[1].shape[0]),
+                   "sample": "bounded: %d contigs of the same length law per step" % n_sample,
+                   "sample_contigs": n_sample, "sample_bases": bases, "seed": SEED},
         "contigs_per_sec": n_sample * args.steps / total,
         "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
                          "sample": "%d contigs / %d bases per step; oracle/phamers_oracle.py (restates scripts/kmer.py:42-50, "
