@@ -778,7 +778,7 @@ __device__ __forceinline__ double warp_min_d(double v) {
 // A warp takes 32 consecutive rows at a time: the cooperative part (gathers, reductions) row by row, then the scalar tail --
 // two square roots, a division and a float64 tanh, ~250 FP64 instructions that would otherwise be issued once per ROW with one
 // useful lane -- once per BATCH with lane = row, followed by coalesced stores.
-__global__ void __launch_bounds__(256) score_decide_kernel(DecideParams p) {
+__global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;

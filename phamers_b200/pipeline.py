@@ -64,10 +64,13 @@ class ContigScorer(object):
 
     def score_fasta(self, path, length_requirement=0, method="combo"):
         from . import fileIO
-        headers, seq, offsets = fileIO.read_fasta_arrays(path)
+        headers, d_seq, d_off = fileIO.read_fasta_arrays_cuda(path)      # records are found on the device; the bases stay there
         ids = np.array([fileIO.get_id(h) for h in headers])
-        scores = self.score_host(seq, offsets, method=method)
+        if len(ids) == 0:
+            return ids, np.zeros((0,), dtype=np.float64)
+        _, d_scores = self.score_device(d_seq, d_off, method=method, return_counts=False)
+        scores = d_scores.cpu().numpy()
         if length_requirement:
-            keep = np.diff(offsets) >= length_requirement                # scripts/phamer.py:154
+            keep = np.diff(d_off.cpu().numpy()) >= length_requirement    # scripts/phamer.py:154
             ids, scores = ids[keep], scores[keep]
         return ids, scores

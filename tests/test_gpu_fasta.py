@@ -111,3 +111,20 @@ def test_count_file_uses_the_device_tokeniser(golden_dir, tmp_path):
     ids, counts = kmer.count_file(str(tricky), 2)
     want = np.stack([po.count_string_np(s, 2) for s in ("AT\tGCGG", "ACGT")])
     assert list(ids) == ["1", "2"] and np.array_equal(counts, want)
+
+
+def test_score_fasta_runs_on_the_device_tokeniser(golden_dir, tmp_path):
+    from phamers_b200 import kmer, phamer, pipeline, references
+    g = np.load(os.path.join(golden_dir, "fasta_golden.npz"))
+    path = tmp_path / "c.fasta"
+    with open(path, "w", newline="") as fh:
+        fh.write(str(g["fasta_text"]))
+    scorer = pipeline.ContigScorer()
+    ids, scores = scorer.score_fasta(str(path))
+    ids2, counts = kmer.count_file(str(path), 4)
+    pos, neg = references.load_reference_features(equalize=True)
+    with np.errstate(invalid="ignore"):
+        want = phamer.score_points(kmer.normalize_counts(counts), pos, neg)
+    assert list(ids) == list(ids2) and np.array_equal(scores, want, equal_nan=True)
+    long_ids, long_scores = scorer.score_fasta(str(path), length_requirement=200)
+    assert len(long_ids) == len(long_scores) <= len(ids)
