@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-contigs", type=int, default=800)
+    ap.add_argument("--cpu-sample-contigs", type=int, default=2400, help="oracle-port sample on rank 0 (about 12 s of one core)")
     return ap.parse_args()
 
 
