@@ -66,7 +66,16 @@ __device__ __forceinline__ uint32_t revcomp_fast(uint32_t y) {
     return x ^ (0x55555555u & ((1u << (2 * K)) - 1u));                 // A<->T, G<->C: low bit of every digit
 }
 
-template <int K, int STRIDE, int WARPS, bool EMIT, bool SWZ>
+// STAGES > 0: the sequence is staged in shared memory by the TMA unit.  Each warp owns STAGES buffers of 512 bytes; lane 0 issues one
+// 1-D bulk copy (cp.async.bulk, completing on an mbarrier) per step, STAGES steps ahead, and every lane then reads its 16 bytes
+// with one conflict-free 128-bit shared-memory load.  The loads in flight no longer cost registers, so the depth can be whatever
+// covers HBM latency with the warps that fit (the big-table kernels, k >= 5, have few).  STAGES = 0: 128-bit streaming loads into
+// a register ring.  MEASURED (1 M contigs, option hist_tma): the staged variant is slower -- k = 4: 6.5 vs 5.1 ms, k = 6 canonical
+// 16.2 vs 12.6 ms -- the loads were never this kernel's limit (the shared-memory atomic pipe is) and every step now also pays an
+// mbarrier wait, a warp barrier and the re-arm; the register ring stays the default.
+constexpr int STAGE_BYTES = 512;
+
+template <int K, int STRIDE, int WARPS, bool EMIT, bool SWZ, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32)
 kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off, int64_t n_contigs,
                  uint32_t *__restrict__ counts, double *__restrict__ freq,
@@ -106,6 +115,19 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
         __syncthreads();
     }
 
+    // TMA staging area: after the tables and their alignment slack
+    uint32_t stg = 0u, bar = 0u, g_issue = 0u, g_wait = 0u;              // steps issued / consumed by this warp so far (same in every lane)
+    if (STAGES > 0) {
+        const uint32_t region = smem_u32(smem_raw) + (uint32_t)WARPS * Cfg::WARP_BYTES + (uint32_t)Cfg::ALIGN;
+        stg = region + (uint32_t)warp * (STAGES * STAGE_BYTES);
+        bar = region + (uint32_t)WARPS * (STAGES * STAGE_BYTES) + (uint32_t)warp * (STAGES * 8);
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) mbar_init(bar + 8u * s, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1ull);
@@ -138,17 +160,50 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
 
                 // PRE 128-bit loads in flight per lane.  The big tables (k >= 5) leave room for few warps per SM, and then the bytes
                 // in flight per SM, not the issue rate, decide whether HBM latency is covered.
-                constexpr int PRE = Cfg::PRE;
-                Dec cur = decode(load(0), 0);
-                uint4 ring[PRE - 1];
+                constexpr int PRE = (STAGES > 0) ? 2 : Cfg::PRE;
+                // TMA path: step `it` = chunks 32 it .. 32 it + 31 of the contig, one bulk copy of up to 512 bytes
+                auto issue = [&](int it) {
+                    const int c_lo = it * 32;
+                    int c_n = nchunks - c_lo;
+                    if (c_n <= 0) return;
+                    c_n = c_n > 32 ? 32 : c_n;
+                    const uint32_t s = g_issue % (STAGES > 0 ? STAGES : 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(bar + 8u * s, (uint32_t)c_n * 16u);
+                        bulk_load(stg + s * STAGE_BYTES, gp + c_lo, (uint32_t)c_n * 16u, bar + 8u * s);
+                    }
+                    ++g_issue;
+                };
+                auto fetch = [&](int it) -> uint4 {
+                    if (it * 32 >= nchunks) return make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t s = g_wait % (STAGES > 0 ? STAGES : 1);
+                    mbar_wait(bar + 8u * s, (g_wait / (STAGES > 0 ? STAGES : 1)) & 1u);
+                    ++g_wait;
+                    return lds_v4(stg + s * STAGE_BYTES + 16u * (uint32_t)lane);     // lanes past the last chunk read stale bytes: decode() blanks them
+                };
+                if (STAGES > 0) {
 #pragma unroll
-                for (int j = 0; j < PRE - 1; ++j) ring[j] = load(1 + j);
+                    for (int j = 0; j < STAGES; ++j) issue(j);
+                }
+                Dec cur = decode(STAGES > 0 ? fetch(0) : load(0), 0);
+                uint4 ring[PRE - 1];
+                if (STAGES == 0) {
+#pragma unroll
+                    for (int j = 0; j < PRE - 1; ++j) ring[j] = load(1 + j);
+                }
 #pragma unroll(PRE - 1)
                 for (int it = 0; it < n_iter; ++it) {
-                    const Dec nxt = decode(ring[0], it + 1);
+                    Dec nxt;
+                    if (STAGES > 0) {
+                        nxt = decode(fetch(it + 1), it + 1);
+                        __syncwarp();                                      // every lane has read (and decoded) the buffer of step `it`
+                        issue(it + STAGES);                                // ... which is refilled with the step STAGES ahead
+                    } else {
+                        nxt = decode(ring[0], it + 1);
 #pragma unroll
-                    for (int j = 0; j + 1 < PRE - 1; ++j) ring[j] = ring[j + 1];
-                    ring[PRE - 2] = load(it + PRE);
+                        for (int j = 0; j + 1 < PRE - 1; ++j) ring[j] = ring[j + 1];
+                        ring[PRE - 2] = load(it + PRE);
+                    }
                     uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
                     const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
                     if (lane == 31) hi_s = wrap_s;
@@ -530,15 +585,16 @@ int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
 int hist_contigs_per_item = 4;
 int hist_stride_for_k5 = 1;          // 2 = k = 5 as 6-mers at every second base (4096-bin window table + 1024-bin direct table per warp): measured slower (10.1 vs 9.1 ms)
 int hist_warps_k6 = 13;
+int hist_tma = 0;                    // 1 = sequence staged in shared memory by TMA bulk copies (k = 4, 5, 6)
 int hist_canonical_swizzle = 1;      // k = 5, 6 canonical: bank-swizzled table + shared-memory look-up table (0 = plain layout, for comparison)
 
-template <int K, int STRIDE, int WARPS, bool EMIT = false, bool SWZ = false>
+template <int K, int STRIDE, int WARPS, bool EMIT = false, bool SWZ = false, int STAGES = 0>
 static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32_t *counts, double *freq,
                        const uint16_t *rc, const uint16_t *compact, int out_bins, unsigned long long *counter,
                        cudaStream_t st, tc::QueryEmit emit = tc::QueryEmit()) {
     using Cfg = HistCfg<K, STRIDE>;
-    const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN;
-    auto kern = kmer_hist_kernel<K, STRIDE, WARPS, EMIT, SWZ>;
+    const size_t smem = (size_t)WARPS * Cfg::WARP_BYTES + Cfg::ALIGN + (size_t)WARPS * STAGES * (STAGE_BYTES + 8);
+    auto kern = kmer_hist_kernel<K, STRIDE, WARPS, EMIT, SWZ, STAGES>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -593,6 +649,8 @@ int launch_count_emit(const uint8_t *seq, const int64_t *off, int64_t n, uint32_
     if (ws_bytes < kCountWorkspaceBytes) { set_error("count workspace too small"); return PHM_E_WORKSPACE; }
     CountWorkspace w = carve(ws);
     PHM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 256, st));
+    if (hist_tma)
+        return launch_hist<4, 2, 8, true, false, 4>(seq, off, n, counts, nullptr, nullptr, nullptr, 256, w.counter, st, emit);
     return launch_hist<4, 2, 8, true>(seq, off, n, counts, nullptr, nullptr, nullptr, 256, w.counter, st, emit);
 }
 
@@ -656,20 +714,25 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
         case 3: return launch_hist<3, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
         case 4:
             if (hist_stride_for_k4 == 2)
-                return launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+                return hist_tma ? launch_hist<4, 2, 8, false, false, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
+                                : launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
         case 5:
             if (hist_stride_for_k5 == 2)
                 return launch_hist<5, 2, 10>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             if (rc && hist_canonical_swizzle)
-                return launch_hist<5, 1, 8, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
-            return launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+                return hist_tma ? launch_hist<5, 1, 8, false, true, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
+                                : launch_hist<5, 1, 8, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            return hist_tma ? launch_hist<5, 1, 8, false, false, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
+                            : launch_hist<5, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
         case 6:
             if (hist_warps_k6 == 4)
                 return launch_hist<6, 1, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             if (rc && hist_canonical_swizzle)
-                return launch_hist<6, 1, 13, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
-            return launch_hist<6, 1, 13>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+                return hist_tma ? launch_hist<6, 1, 11, false, true, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
+                                : launch_hist<6, 1, 13, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            return hist_tma ? launch_hist<6, 1, 11, false, false, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
+                            : launch_hist<6, 1, 13>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
     }
     return PHM_E_ARG;
 }

@@ -101,6 +101,34 @@ __device__ __forceinline__ void sts_v4_zero(uint32_t addr) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
 
+// ---- mbarrier + bulk-copy (TMA) helpers shared by the scorer and the histogram kernel ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();        // a protocol bug must fail loudly, never hang the GPU
+    }
+}
+// 1-D bulk copy global -> shared (16-byte aligned addresses and size), completing `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+
 // RN(a / b) for integer-valued 0 <= a <= b < 2^53 from r = RN(1 / b): q0 = RN(a r) is within 2 ulp, e = a - b q0 is exact (FMA),
 // q0 + e / b = a / b, and a quotient of such integers is never within 2^-93 (relative) of a rounding boundary nor on one, so
 // RN(q0 + e r) is the IEEE quotient numpy computes in kmer.normalize_counts (scripts/kmer.py:219-220).  b = 0 (empty contig):

@@ -253,3 +253,28 @@ def test_k5_k6_kernel_variants_match_oracle(k, option, value, default):
             assert np.array_equal(cfreq.cpu().numpy(), c_oracle.normalize(want_c), equal_nan=True)
     finally:
         _lib.set_option(option, default)
+
+
+@pytest.mark.parametrize("k", [4, 5, 6])
+def test_tma_staged_histogram_matches_oracle(k):
+    """Option hist_tma: the sequence reaches shared memory through cp.async.bulk copies completing on mbarriers (4 stages per
+    warp) instead of 128-bit loads into registers.  Same counts, plain and canonical, on dirty, awkward and long inputs."""
+    from phamers_b200 import ops, _lib
+    rng = np.random.default_rng(4000 + k)
+    seq_a, off_a = _random_workload(rng, 1500, True)
+    lengths = np.array([17, 0, 1, 5, 6, 7, 16, 15, 31, 33, 0, 64, 1000, 7, 511, 512, 513, 2, 300001, 2048, 2049, 100000, 9], dtype=np.int64)
+    off_c = np.concatenate(([0], np.cumsum(lengths)))
+    seq_c = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(off_c[-1]))
+    seq_c[off_c[18] + 150000] = ord("N")
+    _lib.set_option("hist_tma", 1)
+    try:
+        for seq, off in ((seq_a, off_a), (seq_c, off_c)):
+            d_seq, d_off = _device(seq, off)
+            want = c_oracle.count(seq, off, k)
+            counts, freq = ops.count_cuda(d_seq, d_off, k, freq=True)
+            assert np.array_equal(_u32(counts), want)
+            assert np.array_equal(freq.cpu().numpy(), c_oracle.normalize(want), equal_nan=True)
+            canon, _ = ops.count_cuda(d_seq, d_off, k, canonical=True)
+            assert np.array_equal(_u32(canon), po.canonical_fold(want, k))
+    finally:
+        _lib.set_option("hist_tma", 0)
