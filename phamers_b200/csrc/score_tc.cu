@@ -69,7 +69,8 @@ constexpr int TMEM_COLS = 512;            // two sets of (2 halves x 128 columns
 constexpr float SCALE = (float)PREP_SCALE;  // operands are scaled by 2^12 -> accumulator = 2^24 a'.b'
 static_assert(KDIM == PREP_DIM, "score_common.cuh prepares 256-wide rows");
 constexpr int LIST_MAX_ROWS = 16384;      // rows the second ("list") tensor-core pass can take (multiple of MT)
-constexpr int64_t LIST_POOL = (int64_t)1 << 25;   // listed references of all such rows together (4 bytes each); rows that do not fit go to the exhaustive kernels
+constexpr int64_t LIST_POOL = (int64_t)1 << 25;   // most listed references of all such rows together (4 bytes each; the pool is 2048 per
+                                                  // possible row up to this); rows that do not fit go to the exhaustive kernels
 constexpr uint32_t LIST_NO_ROOM = 0xFFFFFFFFu;
 static_assert(LIST_MAX_ROWS % MT == 0, "whole contig tiles");
 constexpr double NORM_SCALE = 8388608.0;  // 2^23: ranking value = 2^23 (|b'|^2 - 2 a'.b')
@@ -967,8 +968,8 @@ __global__ void __launch_bounds__(256) tc_list_gather_kernel(const __half *__res
 }
 
 // exclusive prefix sum of the per-row counts -> ranges in the pool; counts are kept in list_n and cleared for the fill pass
-__global__ void __launch_bounds__(1024) tc_list_scan_kernel(const unsigned long long *list_count, int max_rows, uint32_t *list_cnt,
-                                                            uint32_t *list_n, uint32_t *list_off) {
+__global__ void __launch_bounds__(1024) tc_list_scan_kernel(const unsigned long long *list_count, int max_rows, unsigned long long pool_entries,
+                                                            uint32_t *list_cnt, uint32_t *list_n, uint32_t *list_off) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_base;
     unsigned long long cnt = *list_count;
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(1024) tc_list_scan_kernel(const unsigned long 
         const unsigned long long start = s_base + s_warp[warp] + incl - mine;
         if (i < cnt) {
             list_n[i] = (uint32_t)mine;
-            list_off[i] = (start + mine <= (unsigned long long)LIST_POOL) ? (uint32_t)start : LIST_NO_ROOM;
+            list_off[i] = (start + mine <= pool_entries) ? (uint32_t)start : LIST_NO_ROOM;    // a row that does not fit takes no room at all
             list_cnt[i] = 0u;
         }
         __syncthreads();
@@ -1407,6 +1408,7 @@ struct TcWorkspace {
     unsigned long long *fallback_count; float *stats; unsigned long long *rows_remeasured; PrepConsts *consts;   // one 512-byte header
     unsigned long long *list_count, *rows_listed;
     int list_max_rows;
+    int64_t list_pool_entries;
     int64_t *list_rows; float *list_thr; double *list_km; float *list_crow; uint32_t *list_cnt, *list_n, *list_off, *list_cols; __half *a_list;
     __half *a_op, *b_op;
     float *nbs, *pnorm, *crow;
@@ -1457,7 +1459,9 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.list_cnt = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
     w.list_n = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
     w.list_off = reinterpret_cast<uint32_t *>(take((size_t)lmax * 4));
-    w.list_cols = reinterpret_cast<uint32_t *>(take((size_t)(lmax * 2048 < LIST_POOL ? lmax * 2048 : LIST_POOL) * 4));
+    w.list_pool_entries = lmax * 2048 < LIST_POOL ? lmax * 2048 : LIST_POOL;       // small problems get a small pool (at least 4 M entries)
+    if (w.list_pool_entries < ((int64_t)1 << 22)) w.list_pool_entries = (int64_t)1 << 22;
+    w.list_cols = reinterpret_cast<uint32_t *>(take((size_t)w.list_pool_entries * 4));
     w.a_list = reinterpret_cast<__half *>(take((size_t)lmax * KDIM * 2));
     w.bytes = off;
     return w;
@@ -1620,7 +1624,8 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
             }
             if (rc != PHM_OK) return rc;
             if (pass == 0) {
-                tc_list_scan_kernel<<<1, 1024, 0, st>>>(w.list_count, w.list_max_rows, w.list_cnt, w.list_n, w.list_off);
+                tc_list_scan_kernel<<<1, 1024, 0, st>>>(w.list_count, w.list_max_rows, (unsigned long long)w.list_pool_entries, w.list_cnt,
+                                                        w.list_n, w.list_off);
                 PHM_CUDA_CHECK(cudaGetLastError());
             }
         }
