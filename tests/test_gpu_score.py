@@ -318,3 +318,42 @@ def test_list_pass_settles_overflowed_rows(scoring):
     assert np.array_equal(k5[0], e5[0]) and np.array_equal(k1[0], e1[0])
     assert np.max(np.abs(t_combo - e_combo)) <= 1e-12 and np.max(np.abs(n_combo - e_combo)) <= 1e-12
     assert np.array_equal(t_km, n_km)
+
+
+def test_shapes_around_every_tile_boundary():
+    """Tensor-core path (first pass, list pass, exact decisions) against the exhaustive float64 kernel over shapes that sit on
+    and next to every tile size: 128-row reference tiles, 256-row contig tiles, tiny reference sets (fewer tiles than list-pass
+    slices), one centroid per class, more than a tile of centroids, and k = 1 / 3 / 5; queries are counts or features."""
+    import torch
+    from phamers_b200 import kmer, ops
+    rng = np.random.default_rng(2026)
+    base = rng.dirichlet(np.full(256, 0.7), size=6)                    # a few composition families: dense neighbourhoods
+    def sample(n, depth):
+        fam = rng.integers(0, len(base), size=n)
+        return np.stack([rng.multinomial(int(rng.integers(depth // 2, depth * 2)), base[f]) for f in fam]).astype(np.int64)
+    shapes = [(1, 5, 3, 1, 1, 1), (1, 5, 5, 1, 1, 5), (255, 127, 60, 1, 2, 3), (256, 128, 64, 86, 86, 3), (257, 129, 1, 129, 3, 5),
+              (700, 1000, 999, 130, 86, 1), (513, 384, 100, 86, 256, 3), (40, 4510, 2255, 86, 86, 5)]
+    for n_pts, n_refs, n_pos, n_cp, n_cn, kn in shapes:
+        refs = torch.from_numpy(kmer.normalize_counts(sample(n_refs, 20000))).cuda()
+        cp = torch.from_numpy(kmer.normalize_counts(sample(n_cp, 200000))).cuda()
+        cn = torch.from_numpy(kmer.normalize_counts(sample(n_cn, 200000))).cuda()
+        q_counts = sample(n_pts, 8000)
+        if n_pts > 3:
+            q_counts[2, :] = 0                                          # an empty contig somewhere
+        counts = torch.from_numpy(q_counts.astype(np.int32)).cuda()
+        feats = ops.normalize_cuda(counts)
+        try:
+            ops.set_score_path("tc")
+            t_c = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, kn)]
+            t_f = [t.cpu().numpy() for t in ops.score_cuda(feats, refs, n_pos, cp, cn, kn)]
+            ops.set_score_path("exact")
+            e = [t.cpu().numpy() for t in ops.score_cuda(feats, refs, n_pos, cp, cn, kn)]
+        finally:
+            ops.set_score_path("auto")
+        tag = str((n_pts, n_refs, n_pos, n_cp, n_cn, kn))
+        for got in (t_c, t_f):
+            assert np.array_equal(got[0], e[0], equal_nan=True), tag    # votes
+            ok = ~np.isnan(e[2])
+            assert np.array_equal(np.isnan(got[2]), np.isnan(e[2])), tag
+            assert np.max(np.abs(got[1][ok] - e[1][ok]), initial=0.0) <= 1e-12, tag
+            assert np.max(np.abs(got[2][ok] - e[2][ok]), initial=0.0) <= 1e-12, tag
