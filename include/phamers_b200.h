@@ -167,6 +167,21 @@ int phm_fasta_index(const uint8_t *d_raw, int64_t n_bytes, int64_t *d_result, vo
 int phm_fasta_extract(const uint8_t *d_raw, int64_t n_bytes, const int64_t *d_result, uint8_t *d_seq, int64_t *d_offsets,
                       int64_t *d_header_pos, int64_t max_records, const void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Lloyd iterations of k-means on the device.  Replaces the iterations inside the reference's
+ * KMeans(n_clusters = k, random_state = 10).fit(data).labels_ (learning.kmeans, scripts/learning.py:131-146; run twice per
+ * scoring call, scripts/phamer.py:245-248).  The caller centres the data and seeds the centres exactly as scikit-learn does
+ * (its own k-means++ routine), then:  E step = first argmin of |c|^2 - 2 x.c, M step = cluster means, stop when the labels
+ * stop changing, when the summed squared centre shift is <= tol, or after max_iter; a final E step if the labels had not settled.
+ *     d_x float64[n, dim] (dim <= 1024), d_centres float64[k, dim] in / out, d_labels int32[n] out
+ *     h_info int64[3] (HOST) out: iterations, 1 if the labels settled, 1 if a cluster became empty (scikit-learn relocates empty
+ *     clusters, this call does not: the caller must fall back to the host fit for that case)
+ * SYNCHRONISES the stream once per iteration (convergence is decided on the host from 32 bytes).
+ * ------------------------------------------------------------------------------------------- */
+size_t phm_kmeans_workspace_bytes(int64_t n, int dim, int k);
+int phm_kmeans_lloyd(const double *d_x, int64_t n, int dim, double *d_centres, int k, int max_iter, double tol,
+                     int32_t *d_labels, int64_t *h_info, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostics of the last tensor-core phm_score call that used d_workspace (synchronises `stream`): rows that were
  * re-scored by the exhaustive float64 kernel because their candidate buffer overflowed; stats[0] = largest fraction of a
  * proven error interval used by a true ranking value (<= 1 means the proof held; only collected while option

@@ -35,6 +35,9 @@ SIGNATURES = {
     "phm_count_score": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "phm_score_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "phm_kmeans_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "phm_kmeans_lloyd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
     "phm_fasta_workspace_bytes": (c_size_t, [c_int64]),
     "phm_fasta_index": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "phm_fasta_extract": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -38,6 +38,7 @@ class cross_validator(object):
         self.scoring_function = phamer.score_points
         self.score_threshold = 0
         self.output_directory = "cross_validation"
+        self.kmeans_on_device = False                # True: the k-means fits of every fold iterate on the GPU (references.kmeans_assign_device)
 
     def cross_validate(self):
         """scripts/cross_validate.py:57-101.  Returns (positive_scores, negative_scores)."""
@@ -61,6 +62,17 @@ class cross_validator(object):
 
         self.positive_scores = np.zeros(self.num_positive)
         self.negative_scores = np.zeros(self.num_negative)
+        from . import references
+        saved_kmeans = references.kmeans_on_device
+        references.kmeans_on_device = bool(self.kmeans_on_device) or saved_kmeans
+        try:
+            self._score_folds(positive_asmt, negative_asmt)
+        finally:
+            references.kmeans_on_device = saved_kmeans
+        logger.info("%d-fold cross validation complete." % self.N)
+        return self.positive_scores, self.negative_scores
+
+    def _score_folds(self, positive_asmt, negative_asmt):
         for n in range(self.N):
             logger.info("Iteration %d/%d" % (1 + n, self.N))
             where_positive = (positive_asmt == n)
@@ -72,8 +84,6 @@ class cross_validator(object):
             scores = self.scoring_function(scoring_data, pos_training_data, neg_training_data, method=self.method)
             self.positive_scores[where_positive] = scores[:positive_sub_div_size]
             self.negative_scores[where_negative] = scores[positive_sub_div_size:]
-        logger.info("%d-fold cross validation complete." % self.N)
-        return self.positive_scores, self.negative_scores
 
     def roc(self):
         """(false positive rate, true positive rate, area under the curve) of the cross-validated scores
@@ -119,8 +129,10 @@ def main(argv=None):
     parser.add_argument("-N", "--N_fold", default=20, type=int, help="Number of iteration in N-fold cross validation")
     parser.add_argument("-m", "--method", default="combo", help="Scoring algorithm method")
     parser.add_argument("-equal", "--equalize_reference", action="store_true", help="Use same number of reference data from each")
+    parser.add_argument("--device_kmeans", action="store_true", help="Lloyd iterations of every fold's k-means on the GPU")
     args = parser.parse_args(argv)
     validator = cross_validator()
+    validator.kmeans_on_device = args.device_kmeans
     validator.method = args.method
     validator.N = args.N_fold
     validator.output_directory = args.output_directory

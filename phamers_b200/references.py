@@ -5,9 +5,10 @@ The shipped phage / bacteria tables (reference data/reference_features/{positive
 counts in 'ATGC' order) travel with the package as data/reference_features.npz (tools/pack_reference_features.py).
 
 Clustering of the reference sets is reference-only preprocessing, independent of the contigs being scored
-(scripts/phamer.py:245-248 runs it twice per scoring call, ~1 s each).  It stays on the host with the same
+(scripts/phamer.py:245-248 runs it twice per scoring call, ~1 s each).  By default it stays on the host with the same
 scikit-learn call the reference makes (scripts/learning.py:138: KMeans(n_clusters=k, random_state=10)) so that the
 centroids are the reference's centroids, and it is cached per reference set instead of being redone on every call.
+`kmeans_on_device = True` moves the Lloyd iterations to the GPU (cross validation refits 40 reference subsets).
 """
 import hashlib
 import os
@@ -49,6 +50,43 @@ def kmeans_assign(data, k):
     return np.asarray(KMeans(n_clusters=k, random_state=KMEANS_SEED).fit(data).labels_)
 
 
+kmeans_on_device = False              # True: Lloyd iterations on the GPU (phm_kmeans_lloyd) from scikit-learn's own k-means++ seeding
+
+
+def kmeans_assign_device(data, k):
+    """The same clustering with the Lloyd iterations on the device.  scikit-learn's KMeans.fit centres the data, seeds with its
+    k-means++ routine from RandomState(10) and then iterates (sklearn/cluster/_kmeans.py); here the centring, the tolerance and the
+    seeding are obtained from scikit-learn's own functions (so the random stream is the reference's) and only the iterations run in
+    phm_kmeans_lloyd.  Labels equal scikit-learn's unless a point is equidistant from two centres to ~1e-16; a run in which a
+    cluster becomes empty (scikit-learn relocates it) falls back to the host fit."""
+    import torch
+    import ctypes
+    from sklearn.cluster import _kmeans as skk
+    from sklearn.utils import check_random_state
+    from sklearn.utils.extmath import row_norms
+    from . import _lib, ops
+    lib = _lib.require_cuda()
+    x = np.array(data, dtype=np.float64, order="C", copy=True)
+    n, dim = x.shape
+    if k > n or dim > 1024:
+        return kmeans_assign(data, k)
+    tol = float(skk._tolerance(x, 1e-4))                                      # KMeans(tol=1e-4): mean feature variance * tol
+    x -= x.mean(axis=0)
+    centres, _ = skk._kmeans_plusplus(x, k, x_squared_norms=row_norms(x, squared=True), sample_weight=np.ones(n, dtype=x.dtype),
+                                      random_state=check_random_state(KMEANS_SEED))
+    d_x = torch.from_numpy(x).cuda()
+    d_c = torch.from_numpy(np.ascontiguousarray(centres, dtype=np.float64)).cuda()
+    d_labels = torch.empty((n,), dtype=torch.int32, device="cuda")
+    ws = torch.empty((256,), dtype=torch.uint8, device="cuda")
+    info = (ctypes.c_int64 * 3)()
+    ops.check(lib.phm_kmeans_lloyd(ops.ptr(d_x), n, dim, ops.ptr(d_c), int(k), 300, tol, ops.ptr(d_labels), info, ops.ptr(ws), 256,
+                                   ops.stream_ptr()))
+    ops._launched(2 * int(info[0]) + (0 if info[1] else 1))
+    if info[2]:
+        return kmeans_assign(data, k)
+    return d_labels.cpu().numpy().astype(np.int32)
+
+
 def get_centroids(data, assignment):
     """scripts/learning.py:69-81."""
     labels = sorted(set(assignment) - {-1})
@@ -59,7 +97,7 @@ def cluster_centroids(data, k):
     key = (_digest(data), int(k))
     hit = _centroid_cache.get(key)
     if hit is None:
-        hit = get_centroids(data, kmeans_assign(data, k))
+        hit = get_centroids(data, kmeans_assign_device(data, k) if kmeans_on_device else kmeans_assign(data, k))
         _centroid_cache[key] = hit
     return hit
 

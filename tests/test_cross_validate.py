@@ -49,6 +49,13 @@ def test_cross_validation_matches_reference(golden, tmp_path):
         assert np.max(np.abs(got - want)) <= TOL
         assert np.array_equal(np.sign(got), np.sign(want))
     assert abs(v.roc()[2] - float(golden["auc"])) <= 1e-9
+    # the same folds with every k-means fit iterating on the device: identical clusterings, hence identical scores
+    v2 = cross_validate.cross_validator()
+    v2.method, v2.N, v2.kmeans_on_device = "combo", v.N, True
+    v2.positive_data, v2.negative_data = v.positive_data, v.negative_data
+    np.random.seed(int(golden["seed"]))
+    ps_dev, ns_dev = v2.cross_validate()
+    assert np.array_equal(ps_dev, ps) and np.array_equal(ns_dev, ns)
     v.make_metrics_file()
     v.make_summary_file()
     lines = open(v.get_metric_filename()).read().splitlines()
