@@ -116,35 +116,71 @@ def split_fasta_bytes(raw):
     return ids, data[keep], offsets
 
 
+UPLOAD_CHUNK = 256 << 20             # bytes per pinned staging buffer of the file upload (two buffers alternate)
+
+
+def _upload(buf, n):
+    """File bytes (an mmap, or the bytes of a decompressed .gz) -> CUDA uint8 tensor padded to 16 bytes.  The copy page cache ->
+    pinned staging buffer of chunk i + 1 runs on the host while chunk i crosses PCIe (scripts/kmer.py:131-134 reads the whole
+    file through Python objects instead)."""
+    import torch
+    d_raw = torch.empty(((n + 15) // 16 * 16 + 16,), dtype=torch.uint8, device="cuda")
+    chunk = min(UPLOAD_CHUNK, max(n, 1))
+    stage = [torch.empty((chunk,), dtype=torch.uint8, pin_memory=True) for _ in range(2 if n > chunk else 1)]
+    done = [None] * len(stage)
+    src = np.frombuffer(buf, dtype=np.uint8, count=n)
+    for i, lo in enumerate(range(0, n, chunk)):
+        j = i % len(stage)
+        if done[j] is not None:
+            done[j].synchronize()                                     # the staging buffer's previous upload has left it
+        m = min(chunk, n - lo)
+        stage[j].numpy()[:m] = src[lo:lo + m]
+        d_raw[lo:lo + m].copy_(stage[j][:m], non_blocking=True)
+        done[j] = torch.cuda.Event()
+        done[j].record()
+    torch.cuda.current_stream().synchronize()                         # the staging buffers are released on return
+    return d_raw
+
+
 def read_fasta_arrays_cuda(fasta_file):
-    """Device-side tokenisation of a FASTA file (phm_fasta_index / phm_fasta_extract): the file's bytes go to the GPU once and
-    the sequence bytes never come back.  Returns (titles' first tokens, CUDA uint8 tensor of all sequence bytes end to end
+    """Device-side tokenisation of a FASTA file (phm_fasta_index / phm_fasta_extract): the file is memory-mapped, its bytes go
+    to the GPU once through pinned staging buffers and the sequence bytes never come back; only the title lines are read on the
+    host, at the positions the device reports.  Returns (titles' first tokens, CUDA uint8 tensor of all sequence bytes end to end
     [padded to 16], CUDA int64 offsets[n+1]).  Files holding a tab / VT / FF (stripped by the reference at line ends only) are
     tokenised by the exact host path and uploaded.  Raises IOError when unreadable."""
+    import mmap
     import torch
     from . import ops
-    raw = _open_bytes(fasta_file)
-    n = len(raw)
-    host = torch.empty((max((n + 15) // 16 * 16, 16),), dtype=torch.uint8, pin_memory=True)
-    if n:
-        host[:n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-    if n == 0:
-        return [], torch.zeros((16,), dtype=torch.uint8, device="cuda"), torch.zeros((1,), dtype=torch.int64, device="cuda")
-    d_raw = host.to("cuda", non_blocking=True)                     # allocation padded to 16 bytes, as the scan requires
-    seq, offsets, header_pos, odd = ops.fasta_scan_cuda(d_raw[:n])
-    if odd:
-        ids, h_seq, h_off = split_fasta_bytes(raw)
-        total = int(h_off[-1])
-        pad = torch.zeros((max((total + 15) // 16 * 16, 16),), dtype=torch.uint8)
-        pad[:total] = torch.from_numpy(np.ascontiguousarray(h_seq[:total]).copy()) if total else pad[:0]
-        return ids, pad.cuda(), torch.from_numpy(np.ascontiguousarray(h_off)).cuda()
-    ids = []
-    for hs in header_pos.cpu().tolist():
-        he = raw.find(b"\n", hs)
-        title = raw[hs + 1:(he if he >= 0 else n)].decode("latin-1").rstrip()
-        tokens = title.split(None, 1)
-        ids.append(tokens[0] if tokens else "")
-    return ids, seq, offsets
+    mapped = None
+    if fasta_file.endswith(".gz"):
+        raw = _open_bytes(fasta_file)
+        n = len(raw)
+    else:
+        fh = open(fasta_file, "rb")
+        n = os.fstat(fh.fileno()).st_size
+        raw = mapped = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) if n else b""
+        fh.close()
+    try:
+        if n == 0:
+            return [], torch.zeros((16,), dtype=torch.uint8, device="cuda"), torch.zeros((1,), dtype=torch.int64, device="cuda")
+        d_raw = _upload(raw, n)
+        seq, offsets, header_pos, odd = ops.fasta_scan_cuda(d_raw[:n])
+        if odd:
+            ids, h_seq, h_off = split_fasta_bytes(bytes(raw[:n]))
+            total = int(h_off[-1])
+            pad = torch.zeros((max((total + 15) // 16 * 16, 16),), dtype=torch.uint8)
+            pad[:total] = torch.from_numpy(np.ascontiguousarray(h_seq[:total]).copy()) if total else pad[:0]
+            return ids, pad.cuda(), torch.from_numpy(np.ascontiguousarray(h_off)).cuda()
+        ids = []
+        for hs in header_pos.cpu().tolist():
+            he = raw.find(b"\n", hs)
+            title = bytes(raw[hs + 1:(he if he >= 0 else n)]).decode("latin-1").rstrip()
+            tokens = title.split(None, 1)
+            ids.append(tokens[0] if tokens else "")
+        return ids, seq, offsets
+    finally:
+        if mapped is not None:
+            mapped.close()
 
 
 def read_fasta_arrays(fasta_file):

@@ -128,3 +128,19 @@ def test_score_fasta_runs_on_the_device_tokeniser(golden_dir, tmp_path):
     assert list(ids) == list(ids2) and np.array_equal(scores, want, equal_nan=True)
     long_ids, long_scores = scorer.score_fasta(str(path), length_requirement=200)
     assert len(long_ids) == len(long_scores) <= len(ids)
+
+
+def test_chunked_upload_of_a_file_larger_than_the_staging_buffers(tmp_path, monkeypatch):
+    from phamers_b200 import fileIO
+    rng = np.random.default_rng(3)
+    path = tmp_path / "big.fasta"
+    with open(path, "wb") as fh:
+        for r in range(40):
+            fh.write(b">rec_ID_%d x\n" % r)
+            body = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(100, 9000))).tobytes()
+            fh.write(b"\n".join(body[i:i + 70] for i in range(0, len(body), 70)) + b"\n")
+    monkeypatch.setattr(fileIO, "UPLOAD_CHUNK", 4096 + 16)                 # many chunks, not a multiple of anything convenient
+    headers, d_seq, d_off = fileIO.read_fasta_arrays_cuda(str(path))
+    h_headers, h_seq, h_off = fileIO.read_fasta_arrays(str(path))
+    assert headers == h_headers and np.array_equal(d_off.cpu().numpy(), h_off)
+    assert np.array_equal(d_seq.cpu().numpy()[:int(h_off[-1])], h_seq)
