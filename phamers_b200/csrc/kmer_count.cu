@@ -582,7 +582,8 @@ static EventRing g_hist_ring;        // brackets of the kmer_hist_kernel launche
 int kmer_hist_last_ms(float *ms) { return g_hist_ring.mean_ms(ms); }
 
 int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
-int hist_contigs_per_item = 4;
+int hist_contigs_per_item = 0;          // contigs a warp takes per visit to the work counter; 0 = 1 for k <= 5 (finest balance: 5.03 vs 5.10 ms at
+                                        // k = 4), 4 for k = 6 (12.5 vs 12.8 ms)
 int hist_stride_for_k5 = 1;          // 2 = k = 5 as 6-mers at every second base (4096-bin window table + 1024-bin direct table per warp): measured slower (10.1 vs 9.1 ms)
 int hist_warps_k6 = 13;
 int hist_tma = 0;                    // 1 = sequence staged in shared memory by TMA bulk copies (k = 4, 5, 6)
@@ -600,12 +601,12 @@ static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) { set_error("histogram kernel does not fit on an SM (smem %zu)", smem); return PHM_E_UNSUPPORTED; }
     int64_t grid = (int64_t)per_sm * sm_count();
-    const int64_t items = (n + hist_contigs_per_item - 1) / hist_contigs_per_item;
+    const int per_item = hist_contigs_per_item > 0 ? hist_contigs_per_item : (K >= 6 ? 4 : 1);
+    const int64_t items = (n + per_item - 1) / per_item;
     const int64_t need = (items + WARPS - 1) / WARPS;
     if (grid > need) grid = need < 1 ? 1 : need;
     const bool timed = g_hist_ring.begin(st);
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(seq, off, n, counts, freq, rc, compact, out_bins, counter,
-                                                    hist_contigs_per_item, emit);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(seq, off, n, counts, freq, rc, compact, out_bins, counter, per_item, emit);
     PHM_CUDA_CHECK(cudaGetLastError());
     if (timed) g_hist_ring.end(st);
     return PHM_OK;
@@ -627,11 +628,11 @@ static int launch_hist_packed(const uint32_t *codes, const uint32_t *valid, cons
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) { set_error("packed histogram kernel does not fit on an SM (smem %zu)", smem); return PHM_E_UNSUPPORTED; }
     int64_t grid = (int64_t)per_sm * sm_count();
-    const int64_t items = (n + hist_contigs_per_item - 1) / hist_contigs_per_item;
+    const int per_item = hist_contigs_per_item > 0 ? hist_contigs_per_item : 4;
+    const int64_t items = (n + per_item - 1) / per_item;
     const int64_t need = (items + WARPS - 1) / WARPS;
     if (grid > need) grid = need < 1 ? 1 : need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(codes, valid, off, n, counts, freq, rc, compact, out_bins,
-                                                    counter, hist_contigs_per_item);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(codes, valid, off, n, counts, freq, rc, compact, out_bins, counter, per_item);
     PHM_CUDA_CHECK(cudaGetLastError());
     return PHM_OK;
 }

@@ -82,7 +82,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_canonical_swizzle")) { hist_canonical_swizzle = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_tma")) { hist_tma = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_warps_k6")) { PHM_REQUIRE(value == 4 || value == 13, "4 or 13"); hist_warps_k6 = (int)value; return PHM_OK; }
-    if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 1 && value <= 4096, "1..4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
+    if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 0 && value <= 4096, "0 (automatic) .. 4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_path")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 auto, 1 exact, 2 tensor cores"); score_path = (int)value; return PHM_OK; }
     if (!strcmp(name, "time_kernels")) { time_kernels = value != 0; return PHM_OK; }
     if (!strcmp(name, "score_debug")) { score_debug = (int)value; return PHM_OK; }
