@@ -40,7 +40,7 @@ struct HistCfg {
     static constexpr int DIRECT_BYTES = (STRIDE > 1) ? OUT_BINS * 4 : 0;
     static constexpr int ALIGN = TAB_BYTES < 16 ? 16 : TAB_BYTES;
     static constexpr int WARP_BYTES = ALIGN + DIRECT_BYTES;
-    static constexpr int PRE = TAB_BYTES >= 16384 ? 5 : 2;   // streaming loads in flight per lane
+    static constexpr int PRE = TAB_BYTES >= 16384 ? 5 : 4;   // streaming loads in flight per lane (measured: 2 -> 4 gains 2-3 %, 6 loses occupancy)
 };
 
 // --------------------------------------------------------------------------------------------------
