@@ -242,14 +242,21 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
 
             // ---- fold the window table onto the 4^K bins, staged in `vst`; row total ----
             unsigned long long total = 0;
+            // k = 4 at stride 2: the eight folded bins of a lane stay in registers for the outputs below (only the canonical
+            // gather needs them back in shared memory)
+            constexpr bool KEEP = (STRIDE > 1) && (Cfg::OUT_BINS / 32 <= 8);
+            uint32_t vreg[KEEP ? Cfg::OUT_BINS / 32 : 1];
             if (STRIDE > 1) {
-                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+#pragma unroll(KEEP ? Cfg::OUT_BINS / 32 : 1)
+                for (int i = 0; i < Cfg::OUT_BINS / 32; ++i) {
+                    const int y = lane + 32 * i;
                     uint32_t v = lds_u32(direct + 4u * y);
                     const uint4 q = lds_v4(tab + 16u * y);                 // windows whose first k-mer is y
                     v += q.x + q.y + q.z + q.w;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) v += lds_u32(tab + 4u * (cc * Cfg::OUT_BINS + y));   // ... whose second k-mer is y
-                    sts_u32(direct + 4u * y, v);
+                    if (!KEEP || canonical) sts_u32(direct + 4u * y, v);
+                    if (KEEP) vreg[i] = v;
                     total += v;
                 }
             } else if (Cfg::OUT_BINS >= 128) {
@@ -267,10 +274,19 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
             __syncwarp();
 
             if (!canonical) {
-                for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
-                    const uint32_t v = lds_u32(vst + 4u * y);
-                    if (counts) counts[c * Cfg::OUT_BINS + y] = v;
-                    if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)v, dtotal, rtotal);
+                if (KEEP) {
+#pragma unroll
+                    for (int i = 0; i < (KEEP ? Cfg::OUT_BINS / 32 : 1); ++i) {
+                        const int y = lane + 32 * i;
+                        if (counts) counts[c * Cfg::OUT_BINS + y] = vreg[i];
+                        if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)vreg[i], dtotal, rtotal);
+                    }
+                } else {
+                    for (int y = lane; y < Cfg::OUT_BINS; y += 32) {
+                        const uint32_t v = lds_u32(vst + 4u * y);
+                        if (counts) counts[c * Cfg::OUT_BINS + y] = v;
+                        if (freq) freq[c * Cfg::OUT_BINS + y] = exact_quotient((double)v, dtotal, rtotal);
+                    }
                 }
                 if (EMIT) {
                     // same arithmetic, element order and reduction order as tc_prep_rows_kernel on (count / total)
@@ -278,7 +294,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
 #pragma unroll
                     for (int i = 0; i < Cfg::OUT_BINS / 32; ++i) {
                         const int y = lane + 32 * i;
-                        const double x = exact_quotient((double)lds_u32(vst + 4u * y), dtotal, rtotal);
+                        const double x = exact_quotient((double)(KEEP ? vreg[KEEP ? i : 0] : lds_u32(vst + 4u * y)), dtotal, rtotal);
                         emit.op[c * Cfg::OUT_BINS + y] = tc::prep_accumulate(x, s, sc, sd, sh);
                     }
 #pragma unroll
