@@ -204,9 +204,9 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                         for (int j = 0; j + 1 < PRE - 1; ++j) ring[j] = ring[j + 1];
                         ring[PRE - 2] = load(it + PRE);
                     }
-                    uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
-                    const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
-                    if (lane == 31) hi_s = wrap_s;
+                    // the 16 bases that follow this lane's: the next lane's chunk, and for lane 31 lane 0's chunk of the NEXT step --
+                    // one rotating shuffle in which lane 0 offers its next chunk (nobody needs its current one)
+                    const uint32_t hi_s = __shfl_sync(FULL, lane == 0 ? nxt.s : cur.s, (lane + 1) & 31);
                     const bool dirty = (cur.blank != 0u) | ((lane == 0) & (nxt.blank != 0u));
                     if (!__any_sync(FULL, dirty)) {
 #pragma unroll
@@ -215,9 +215,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                             red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : woff));
                         }
                     } else {
-                        uint32_t hi_b = __shfl_down_sync(FULL, cur.blank, 1);
-                        const uint32_t wrap_b = __shfl_sync(FULL, nxt.blank, 0);
-                        if (lane == 31) hi_b = wrap_b;
+                        const uint32_t hi_b = __shfl_sync(FULL, lane == 0 ? nxt.blank : cur.blank, (lane + 1) & 31);
 #pragma unroll
                         for (int p = 0; p < 16; p += STRIDE) {
                             const uint32_t bl = window_bits<W>(cur.blank, hi_b, p);
@@ -517,17 +515,15 @@ kmer_hist_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__re
                 Dec cur = fetch(0);
                 for (int it = 0; it < n_iter; ++it) {
                     const Dec nxt = fetch(it + 1);
-                    uint32_t hi_s = __shfl_down_sync(FULL, cur.s, 1);
-                    const uint32_t wrap_s = __shfl_sync(FULL, nxt.s, 0);
-                    if (lane == 31) hi_s = wrap_s;
+                    // the 16 bases that follow this lane's: the next lane's chunk, and for lane 31 lane 0's chunk of the NEXT step --
+                    // one rotating shuffle in which lane 0 offers its next chunk (nobody needs its current one)
+                    const uint32_t hi_s = __shfl_sync(FULL, lane == 0 ? nxt.s : cur.s, (lane + 1) & 31);
                     const bool dirty = (cur.blank != 0u) | ((lane == 0) & (nxt.blank != 0u));
                     if (!__any_sync(FULL, dirty)) {
 #pragma unroll
                         for (int p = 0; p < 16; ++p) red_shared_inc(tab | window_offset<K>(cur.s, hi_s, p));
                     } else {
-                        uint32_t hi_b = __shfl_down_sync(FULL, cur.blank, 1);
-                        const uint32_t wrap_b = __shfl_sync(FULL, nxt.blank, 0);
-                        if (lane == 31) hi_b = wrap_b;
+                        const uint32_t hi_b = __shfl_sync(FULL, lane == 0 ? nxt.blank : cur.blank, (lane + 1) & 31);
 #pragma unroll
                         for (int p = 0; p < 16; ++p)
                             if (window_bits<K>(cur.blank, hi_b, p) == 0u) red_shared_inc(tab + window_offset<K>(cur.s, hi_s, p));
