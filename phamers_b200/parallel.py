@@ -28,6 +28,10 @@ def gather_scores(local_scores, counts_per_rank, group=None):
     world = dist.get_world_size(group)
     counts_per_rank = [int(c) for c in counts_per_rank]
     width = max(counts_per_rank) if counts_per_rank else 0
+    if counts_per_rank and min(counts_per_rank) == width and local_scores.is_contiguous():
+        out = torch.empty((world * width,), dtype=local_scores.dtype, device=local_scores.device)     # equal shards: no padding, no copy
+        dist.all_gather_into_tensor(out, local_scores, group=group)
+        return out
     padded = torch.zeros((width,), dtype=local_scores.dtype, device=local_scores.device)
     padded[:local_scores.numel()] = local_scores
     out = torch.empty((world * width,), dtype=local_scores.dtype, device=local_scores.device)
