@@ -61,6 +61,10 @@ def _worker(rank, world, port, n_contigs, out_dir):
         counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
         gathered = parallel.gather_scores(local, counts)
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), gathered.numpy())
+        # equal shards (what bench.py has: a fixed number of contigs per GPU) take the path without padding
+        same = torch.arange(rank * 50, (rank + 1) * 50, dtype=torch.float64)
+        equal = parallel.gather_scores(same, [50] * world)
+        assert torch.equal(equal, torch.arange(0, 50 * world, dtype=torch.float64))
     finally:
         dist.destroy_process_group()
 
