@@ -200,21 +200,36 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // 
 // INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
 template <int K, int CAP, bool INSERT, bool LABELLED>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
-                                           int n_class, float C, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
+                                           int n_class, float C, float Cpm, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
                                            uint32_t &flags, float (&drop_lo)[2]) {
     float lo[32], gm[8];
+    // Quick reject with ONE constant per row instead of P_j per column: lo_j = RN(d_j - C P_j) >= RD(min_j d_j - RU(C pmax)) because
+    // P_j <= pmax and rounding is monotone, so if that bound is already above the threshold in every lane the chunk has no hit and
+    // neither the P_j loads nor the 32 multiply-adds are needed (Cpm = RU(C * pmax), pmax = the largest P of the reference set).
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
         const uint4 nb = lds_v4(nbs_c + 16u * g);
+        lo[4 * g + 0] = __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]);
+        lo[4 * g + 1] = __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]);
+        lo[4 * g + 2] = __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]);
+        lo[4 * g + 3] = __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]);
+        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
+    }
+    const float limit0 = u[K - 1];
+    {
+        const float m0 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+        if (!__any_sync(FULL, __fsub_rd(m0, Cpm) <= limit0)) return;
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
         const uint4 pp = lds_v4(p_c + 16u * g);
-        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]));
-        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]));
-        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]));
-        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]));
+        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), lo[4 * g + 0]);
+        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), lo[4 * g + 1]);
+        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), lo[4 * g + 2]);
+        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), lo[4 * g + 3]);
         gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
     }
     const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-    const float limit0 = u[K - 1];
     if (!__any_sync(FULL, m <= limit0)) return;
 
     // sign of (limit - lo) shifted in column by column: column 0 ends in the top bit, a clear bit is a hit (lo <= limit)
@@ -275,7 +290,7 @@ __device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nb
 // would be a hit; instead all 128 upper bounds go through the insertion network first and the hits are collected in a second
 // sweep over the same accumulators (they stay in tensor memory until the set is released).
 template <int K, int CAP, bool TWO_PASS, bool LABELLED>
-__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C,
+__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float Cpm,
                                           uint32_t cand_addr, int first, float (&u)[K], int &cnt, uint32_t &flags, float (&drop_lo)[2]) {
     uint32_t ra[32], rb[32];
     __syncwarp();                                      // tcgen05.ld is .sync.aligned: the warp must be converged
@@ -296,18 +311,18 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
         tmem_wait_ld();
     }
     tmem_ld32_issue(taddr + 32u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 64u, ra);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 96u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
     tmem_wait_ld();
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
+    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
 }
 
 // ---------------- list mode: second pass over the rows whose candidate buffer overflowed ----------------
@@ -318,17 +333,29 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
 // prefix sum (tc_list_scan_kernel) gives every row its range in one shared pool, then the same pass FILLS the ranges
 // (cols != nullptr).  Lists are usually short (the interval is ~1 % of the distance) but a contig far from every reference
 // can have thousands of references inside it; only rows that do not fit in the pool go to the exhaustive kernels.
-__device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c, int n_class, float C,
+__device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c, int n_class, float C, float Cpm,
                                            float T, uint32_t *cnt, uint32_t *cols) {
     float lo[32], gm[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 8; ++g) {                                        // quick reject with the per-row constant, as in scan_chunk
         const uint4 nb = lds_v4(nbs_c + 16u * g);
+        lo[4 * g + 0] = __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]);
+        lo[4 * g + 1] = __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]);
+        lo[4 * g + 2] = __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]);
+        lo[4 * g + 3] = __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]);
+        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
+    }
+    {
+        const float m0 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+        if (!__any_sync(FULL, __fsub_rd(m0, Cpm) <= T)) return;
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
         const uint4 pp = lds_v4(p_c + 16u * g);
-        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]));
-        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]));
-        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]));
-        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]));
+        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), lo[4 * g + 0]);
+        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), lo[4 * g + 1]);
+        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), lo[4 * g + 2]);
+        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), lo[4 * g + 3]);
         gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
     }
     const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
@@ -346,25 +373,25 @@ __device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs
     }
 }
 
-__device__ __forceinline__ void list_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float T,
+__device__ __forceinline__ void list_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float Cpm, float T,
                                           uint32_t *cnt, uint32_t *cols) {
     uint32_t ra[32], rb[32];
     __syncwarp();
     tmem_ld32_issue(taddr, ra);
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 32u, rb);
-    list_chunk(ra, nbs_addr, p_addr, col0, n_class, C, T, cnt, cols);
+    list_chunk(ra, nbs_addr, p_addr, col0, n_class, C, Cpm, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 64u, ra);
-    list_chunk(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, T, cnt, cols);
+    list_chunk(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, Cpm, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 96u, rb);
-    list_chunk(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, T, cnt, cols);
+    list_chunk(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, Cpm, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
-    list_chunk(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, T, cnt, cols);
+    list_chunk(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, Cpm, T, cnt, cols);
 }
 
 struct TcParams {
@@ -376,6 +403,7 @@ struct TcParams {
     const float *nbs;                    // [(nt_ref + nt_pos + nt_neg) * 128] 2^23 |b'|^2, PAD_NORM on padding rows
     const float *pnorm;                  // same layout: P_j = |B~_j| rounded up, 0 on padding rows
     const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
+    const PrepConsts *consts;            // rho and pmax of the reference set (device)
     uint2 *cand;                         // [n_points, 16] (lower bound as float bits, column within its class)
     float *cand_up;                      // [n_points, 16] matching upper bounds (lower + 2 C P)
     int ref_pad, cp_pad;                 // offsets of the centroid classes in nbs / pnorm
@@ -538,6 +566,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
             const bool live = C >= 0.0f;                           // false for padding rows and NaN feature rows
             const float init = live ? INFINITY : -INFINITY;        // -inf: nothing ever qualifies
             if (!live) C = 0.0f;
+            const float Cpm = __fmul_ru(C, p.consts->pmax);        // quick-reject constant of scan_chunk
             if constexpr (LIST) {
                 const int sl = item - mt * sched.n_slices;
                 const int nt_lo = (int)((long long)p.nt_ref * sl / sched.n_slices), nt_hi = (int)((long long)p.nt_ref * (sl + 1) / sched.n_slices);
@@ -556,7 +585,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                     mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
-                    list_tile(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, T, my_cnt, my_cols);
+                    list_tile(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, Cpm, T, my_cnt, my_cols);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -579,17 +608,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
                 if (p.debug == 1) {
                 } else if (nt == 0)
-                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
+                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, Cpm, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt < p.nt_ref)
-                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
+                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, Cpm, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt == p.nt_ref)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, Cpm, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt < p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, Cpm, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt == p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, Cpm, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 else
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, Cpm, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -1574,7 +1603,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
-    p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo; p.thr_out = w.thr_out;
+    p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.consts = w.consts; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo; p.thr_out = w.thr_out;
     p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
     p.debug = score_debug;
     p.list_count = w.list_count; p.list_max_rows = w.list_max_rows; p.list_thr = w.list_thr; p.list_cnt = w.list_cnt;
