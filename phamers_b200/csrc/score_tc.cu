@@ -821,9 +821,10 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
             const bool is_neg = lane >= CAP_R + CAP_C && lane < CAP_R + CAP_C + cnt_n && lane < NENT;
             const int col = (int)ent.y;
             const bool valid = is_ref || is_pos || is_neg;
-            const double lower = valid ? (double)__uint_as_float(ent.x) : INFINITY;
-            const double upper = valid ? (double)up_f : INFINITY;
-            const double width = valid ? upper - lower : 0.0;
+            // the bounds are float values: every comparison below is exact in float (single shuffles, no float64 compares)
+            const float lower = valid ? __uint_as_float(ent.x) : INFINITY;
+            const float upper = valid ? up_f : INFINITY;
+            const double width = valid ? (double)upper - (double)lower : 0.0;
             int my_idx = col;                                          // index in the caller's arrays
             if (is_ref) my_idx = (int)((p.perm_a * (int64_t)col + p.perm_c) % p.n_refs);
 
@@ -832,16 +833,16 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
                 int rank = 0;                                          // position of my upper bound among the candidates'
 #pragma unroll
                 for (int s = 0; s < CAP_R; ++s) {
-                    const double ou = __shfl_sync(FULL, upper, s);
+                    const float ou = __shfl_sync(FULL, upper, s);
                     if (s < cnt_r && s != lane && (ou < upper || (ou == upper && s < lane))) ++rank;
                 }
                 const unsigned kth = __ballot_sync(FULL, is_ref && rank == kn - 1);
-                const double u_k = __shfl_sync(FULL, upper, __ffs(kth) - 1);
+                const float u_k = __shfl_sync(FULL, upper, __ffs(kth) - 1);
                 const bool in_band = is_ref && lower <= u_k;
                 const unsigned band = __ballot_sync(FULL, in_band);
                 const unsigned pos_mask = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
                 const int n_band = __popc(band);
-                const bool lost_neg = (double)dropped.x <= u_k, lost_pos = (double)dropped.y <= u_k;
+                const bool lost_neg = dropped.x <= u_k, lost_pos = dropped.y <= u_k;
                 if (lost_neg || lost_pos) {
                     // a dropped candidate could still be among the k nearest: only a unanimous vote over kept AND dropped ones
                     // can be read off
@@ -883,7 +884,7 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
                 for (int s = 0; s < CAP_R; ++s) {
                     if (s >= cnt_r) break;
                     const int idx = __shfl_sync(FULL, my_idx, s);
-                    const double lo_s = __shfl_sync(FULL, lower, s), w_s = __shfl_sync(FULL, width, s);
+                    const double lo_s = (double)__shfl_sync(FULL, lower, s), w_s = __shfl_sync(FULL, width, s);
                     const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
                     const double exact = (d - na) * NORM_SCALE;                 // what the ranking value estimates
                     const double err = fabs(lo_s + 0.5 * w_s - exact);
@@ -898,7 +899,12 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
             // ---------------- nearest centroid of each class ----------------
             if (has_cent) {
                 double e2[2] = {INFINITY, INFINITY};
-                const double u_p = warp_min_d(is_pos ? upper : INFINITY), u_n = warp_min_d(is_neg ? upper : INFINITY);
+                float u_p = is_pos ? upper : INFINITY, u_n = is_neg ? upper : INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    u_p = fminf(u_p, __shfl_xor_sync(FULL, u_p, o));
+                    u_n = fminf(u_n, __shfl_xor_sync(FULL, u_n, o));
+                }
                 unsigned rest_p = __ballot_sync(FULL, is_pos && lower <= u_p);
                 unsigned rest_n = __ballot_sync(FULL, is_neg && lower <= u_n);
                 if (cent_overflow || cnt_p < 1 || cnt_n < 1) {
