@@ -193,7 +193,17 @@ def test_properties_at_scale():
     host_seq = seq[:end].cpu().numpy()
     host_off = off[:n + 1].cpu().numpy()
     assert np.array_equal(c4[:n], c_oracle.count(host_seq, host_off, 4))
+    # BASELINE configs[1] / [2] at full size (1 M contigs, 16 Gbases): row sums of clean contigs, every k, plain and canonical
+    del counts4, freq4, naive, s1
+    seq, off = ops.synth_contigs(20260101, 0, 1000000)
+    lengths = (off[1:] - off[:-1])
+    for k in (4, 5, 6):
+        for canonical in (False, True):
+            ck, _ = ops.count_cuda(seq, off, k, canonical=canonical)
+            assert torch.equal(ck.sum(dim=1, dtype=torch.int64), lengths - (k - 1)), (k, canonical)
+            del ck
     # determinism of the generator across shards
+    seq, off = ops.synth_contigs(20260101, 0, 20000)
     seq2, off2 = ops.synth_contigs(20260101, 100, 50)
     a0, a1 = int(off[100].item()), int(off[150].item())
     assert torch.equal(seq2, seq[a0:a1])

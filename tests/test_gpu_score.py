@@ -166,7 +166,7 @@ def test_scoring_from_counts_equals_scoring_from_features(scoring):
 
 
 def test_full_path_properties_at_scale(scoring):
-    """BASELINE configs[1] shape at a size the GPU finishes in a blink (300k synthetic contigs, 4.8 Gbases): properties that
+    """BASELINE configs[1] at its full size (1 M synthetic contigs, 16 Gbases, one B200): properties that
     do not need an oracle run of the whole thing -- shard invariance (the multi-GPU layout must not change a single score),
     the tensor-core path against the exhaustive float64 kernel on a sample of rows, the kNN term being exactly +-1, the
     centroid term inside tanh's range for this metric, and a small prefix against the CPU oracle end to end."""
@@ -176,7 +176,7 @@ def test_full_path_properties_at_scale(scoring):
     g, pos, neg = scoring
     cents = (np.ascontiguousarray(g["centroids_pos"]), np.ascontiguousarray(g["centroids_neg"]))
     scorer = pipeline.ContigScorer(pos, neg, centroids=cents)
-    n = 300000
+    n = 1000000
     seq, off = ops.synth_contigs(20260101, 0, n)
     counts, combo = scorer.score_device(seq, off)
     assert ops.score_stats()["fallback_rows"] <= 100                # read before another path reuses the workspace
@@ -188,7 +188,7 @@ def test_full_path_properties_at_scale(scoring):
 
     # shard invariance: three uneven shards scored separately give the same bits as the whole
     pieces = []
-    for lo, hi in ((0, 70001), (70001, 70002), (70002, n)):
+    for lo, hi in ((0, 270001), (270001, 270002), (270002, n)):
         o = (off[lo:hi + 1] - off[lo]).contiguous()
         s = seq[int(off[lo]):int(off[hi])]
         if s.data_ptr() % 16:                                       # the C-ABI wants a 16-byte aligned sequence buffer
