@@ -191,7 +191,7 @@ int phm_kmeans_lloyd(const double *d_x, int64_t n, int dim, double *d_centres, i
 int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max_rank_error, void *stream);
 
 /* Tuning / path selection for experiments and tests (defaults are the measured best; every variant gives the same results).
- * Options: "hist_stride_k4" (2 | 1: 5-mer windows at every second base | plain 4-mers), "hist_stride_k5" (1 | 2),
+ * Options: "hist_stride_k4" (2 | 1: 5-mer windows at every second base | plain 4-mers), "hist_stride_k5" (0 = automatic | 1 | 2: 6-mer windows in 16-bit packed counters),
  * "hist_warps_k6" (13 | 4), "hist_contigs_per_item" (0 = automatic), "hist_canonical_swizzle" (1 | 0: bank-swizzled table for the
  * canonical fold at k = 5, 6), "hist_tma" (0 | 1: sequence staged in shared memory by cp.async.bulk),
  * "score_list_pass" (0 = overflowed rows skip the listing pass and go to the exhaustive kernels),

@@ -35,12 +35,13 @@ template <int K, int STRIDE>
 struct HistCfg {
     static constexpr int W = K + STRIDE - 1;             // window width in bases
     static constexpr int TAB_BINS = 1 << (2 * W);
-    static constexpr int TAB_BYTES = TAB_BINS * 4;
+    static constexpr bool PACKED = (K == 5 && STRIDE == 2);   // 6-mer windows in 16-bit counters, two per word (fold6_k5)
+    static constexpr int TAB_BYTES = PACKED ? TAB_BINS * 2 : TAB_BINS * 4;
     static constexpr int OUT_BINS = 1 << (2 * K);
     static constexpr int DIRECT_BYTES = (STRIDE > 1) ? OUT_BINS * 4 : 0;
     static constexpr int ALIGN = TAB_BYTES < 16 ? 16 : TAB_BYTES;
     static constexpr int WARP_BYTES = ALIGN + DIRECT_BYTES;
-    static constexpr int PRE = TAB_BYTES >= 16384 ? 5 : 4;   // streaming loads in flight per lane (measured: 2 -> 4 gains 2-3 %, 6 loses occupancy)
+    static constexpr int PRE = (TAB_BYTES >= 16384 || PACKED) ? 5 : 4;   // streaming loads in flight per lane (measured: 2 -> 4 gains 2-3 %, 6 loses occupancy)
 };
 
 // --------------------------------------------------------------------------------------------------
@@ -64,6 +65,71 @@ __device__ __forceinline__ uint32_t revcomp_fast(uint32_t y) {
     uint32_t x = __brev(y) >> (32 - 2 * K);                            // digits reversed, the two bits of each digit swapped
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
     return x ^ (0x55555555u & ((1u << (2 * K)) - 1u));                 // A<->T, G<->C: low bit of every digit
+}
+
+// --------------------------------------------------------------------------------------------------
+// k = 5 as 6-mer windows at every second base, 16-bit counters packed two per word (bin 2w in the low half of word w, bin 2w + 1 in
+// the high half): 8 instead of 16 atomics per step and an 8 KB table.  A step adds at most 8 * 32 = 256 to a counter and the table is
+// folded at least every FOLD6_STEPS = 248 steps, so no counter and no partial sum of counters passes 63488: the marginal sums are plain
+// 32-bit adds on packed halves.  fold6_k5 adds both marginals of the table to the 1024-bin table `direct` and zeroes the 6-mer table.
+// Lane l reads words 4l..4l+3 of each of the 16 rows q (128 words per row): bins q*256 + 8l + 2j + h.
+//   first 5-mer   x = bin >> 2   = q * 64 + 2l + (j >> 1)          sum over j & 1, h
+//   second 5-mer  x = bin & 1023 = (q & 3) * 256 + 8l + 2j + h     sum over q >> 2
+// --------------------------------------------------------------------------------------------------
+constexpr int FOLD6_STEPS = 248;
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t hsum16(uint32_t x) { return (x & 0xFFFFu) + (x >> 16); }
+
+__device__ __forceinline__ void fold6_k5(uint32_t tab, uint32_t direct, int lane) {
+    __syncwarp();
+    uint4 S[4];                          // S[q & 3] = sum over q >> 2 of row q, packed halves
+#pragma unroll
+    for (int b = 0; b < 4; ++b) S[b] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const uint32_t a = tab + (uint32_t)(q * 512 + lane * 16);
+        const uint4 w = lds_v4(a);
+        sts_v4_zero(a);                  // only this lane ever reads these 16 bytes during a fold
+        S[q & 3].x += w.x; S[q & 3].y += w.y; S[q & 3].z += w.z; S[q & 3].w += w.w;
+        const uint32_t d = direct + (uint32_t)(q * 256 + lane * 8);      // first 5-mer: x = q * 64 + 2l, 2l + 1
+        uint2 u = lds_v2(d);
+        u.x += hsum16(w.x + w.y);
+        u.y += hsum16(w.z + w.w);
+        sts_v2(d, u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {                                        // second 5-mer: x = b * 256 + 8l .. 8l + 7
+        const uint32_t d = direct + (uint32_t)(b * 1024 + lane * 32);
+        uint4 u = lds_v4(d), v = lds_v4(d + 16u);
+        u.x += S[b].x & 0xFFFFu; u.y += S[b].x >> 16; u.z += S[b].y & 0xFFFFu; u.w += S[b].y >> 16;
+        v.x += S[b].z & 0xFFFFu; v.y += S[b].z >> 16; v.z += S[b].w & 0xFFFFu; v.w += S[b].w >> 16;
+        sts_v4(d, u); sts_v4(d + 16u, v);
+    }
+    __syncwarp();
+}
+
+// the field's lowest bit lands on bit `lsb` of the result (bits outside the field are not masked)
+template <int WW>
+__device__ __forceinline__ uint32_t window_raw(uint32_t cur, uint32_t nxt, int p, int lsb) {
+    const int sh = 64 - 2 * p - 2 * WW - lsb;
+    if (sh >= 32) return cur >> (sh - 32);
+    return funnel_r(nxt, cur, (uint32_t)sh);
+}
+// one 6-mer window into the packed table: word (bin >> 1), half (bin & 1)
+__device__ __forceinline__ void post6(uint32_t tab, uint32_t raw1) {       // raw1 = window_raw<6>(.., lsb = 1)
+    red_shared_add(tab | (raw1 & 0x1FFCu), (raw1 & 2u) ? 0x10000u : 1u);
 }
 
 // STAGES > 0: the sequence is staged in shared memory by the TMA unit.  Each warp owns STAGES buffers of 512 bytes; lane 0 issues one
@@ -95,8 +161,8 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
     float emit_rho = 0.f, emit_pmax = 0.f;
     if (EMIT) { emit_rho = emit.consts->rho; emit_pmax = emit.consts->pmax; }
 
-    if (Cfg::TAB_BINS >= 128) {
-        for (int i = lane; i < Cfg::TAB_BINS / 4; i += 32) sts_v4_zero(tab + 16u * i);
+    if (Cfg::TAB_BYTES >= 512) {
+        for (int i = lane; i < Cfg::TAB_BYTES / 16; i += 32) sts_v4_zero(tab + 16u * i);
     } else {
         for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
     }
@@ -211,8 +277,12 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                     if (!__any_sync(FULL, dirty)) {
 #pragma unroll
                         for (int p = 0; p < 16; p += STRIDE) {
-                            const uint32_t woff = window_offset<W>(cur.s, hi_s, p);
-                            red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : woff));
+                            if (Cfg::PACKED) {
+                                post6(tab, window_raw<6>(cur.s, hi_s, p, 1));
+                            } else {
+                                const uint32_t woff = window_offset<W>(cur.s, hi_s, p);
+                                red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : woff));
+                            }
                         }
                     } else {
                         const uint32_t hi_b = __shfl_sync(FULL, lane == 0 ? nxt.blank : cur.blank, (lane + 1) & 31);
@@ -221,7 +291,8 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                             const uint32_t bl = window_bits<W>(cur.blank, hi_b, p);
                             const uint32_t idx = window_bits<W>(cur.s, hi_s, p);
                             if (bl == 0u) {
-                                red_shared_inc(tab + (SWZ ? swz_off<K>(4u * idx) : 4u * idx));
+                                if (Cfg::PACKED) post6(tab, idx << 1);
+                                else red_shared_inc(tab + (SWZ ? swz_off<K>(4u * idx) : 4u * idx));
                             } else if (STRIDE > 1) {
                                 // a partly blank window still holds up to STRIDE clean k-mers
 #pragma unroll
@@ -234,6 +305,7 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
                         }
                     }
                     cur = nxt;
+                    if (Cfg::PACKED && (it % FOLD6_STEPS) == FOLD6_STEPS - 1 && it + 1 < n_iter) fold6_k5(tab, direct, lane);
                 }
             }
             __syncwarp();
@@ -244,7 +316,13 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
             // gather needs them back in shared memory)
             constexpr bool KEEP = (STRIDE > 1) && (Cfg::OUT_BINS / 32 <= 8);
             uint32_t vreg[KEEP ? Cfg::OUT_BINS / 32 : 1];
-            if (STRIDE > 1) {
+            if (Cfg::PACKED) {
+                if (end - start >= K) fold6_k5(tab, direct, lane);
+                for (int i = lane; i < Cfg::OUT_BINS / 4; i += 32) {
+                    const uint4 q = lds_v4(direct + 16u * i);
+                    total += (unsigned long long)q.x + q.y + q.z + q.w;
+                }
+            } else if (STRIDE > 1) {
 #pragma unroll(KEEP ? Cfg::OUT_BINS / 32 : 1)
                 for (int i = 0; i < Cfg::OUT_BINS / 32; ++i) {
                     const int y = lane + 32 * i;
@@ -332,8 +410,9 @@ kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
             }
             __syncwarp();
 
-            // ---- clear for the next contig ----
-            if (Cfg::TAB_BINS >= 128) {
+            // ---- clear for the next contig (the packed table was zeroed by its fold) ----
+            if (Cfg::PACKED) {
+            } else if (Cfg::TAB_BINS >= 128) {
                 for (int i = lane; i < Cfg::TAB_BINS / 4; i += 32) sts_v4_zero(tab + 16u * i);
             } else {
                 for (int i = lane; i < Cfg::TAB_BINS; i += 32) sts_u32(tab + 4u * i, 0u);
@@ -596,7 +675,8 @@ int kmer_hist_last_ms(float *ms) { return g_hist_ring.mean_ms(ms); }
 int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
 int hist_contigs_per_item = 0;          // contigs a warp takes per visit to the work counter; 0 = 1 for k <= 5 (finest balance: 5.03 vs 5.10 ms at
                                         // k = 4), 4 for k = 6 (12.5 vs 12.8 ms)
-int hist_stride_for_k5 = 1;          // 2 = k = 5 as 6-mers at every second base (4096-bin window table + 1024-bin direct table per warp): measured slower (10.1 vs 9.1 ms)
+int hist_stride_for_k5 = 0;          // 0 = automatic: 6-mers at every second base in 16-bit packed counters for plain bins (7.96 vs 8.22 ms),
+                                     // plain 5-mers on the bank-swizzled table for canonical bins (7.70 vs 8.90 ms); 1 | 2 force one
 int hist_warps_k6 = 13;
 int hist_tma = 0;                    // 1 = sequence staged in shared memory by TMA bulk copies (k = 4, 5, 6)
 int hist_canonical_swizzle = 1;      // k = 5, 6 canonical: bank-swizzled table + shared-memory look-up table (0 = plain layout, for comparison)
@@ -731,8 +811,8 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
                                 : launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
         case 5:
-            if (hist_stride_for_k5 == 2)
-                return launch_hist<5, 2, 10>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
+            if (hist_stride_for_k5 == 2 || (hist_stride_for_k5 == 0 && !rc))
+                return launch_hist<5, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);
             if (rc && hist_canonical_swizzle)
                 return hist_tma ? launch_hist<5, 1, 8, false, true, 4>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st)
                                 : launch_hist<5, 1, 8, false, true>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w.counter, st);

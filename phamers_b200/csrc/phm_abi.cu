@@ -78,7 +78,7 @@ extern "C" int phm_device_caps(phm_caps *out) {
 extern "C" int phm_set_option(const char *name, int64_t value) {
     PHM_REQUIRE(name != nullptr, "name is null");
     if (!strcmp(name, "hist_stride_k4")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k4 = (int)value; return PHM_OK; }
-    if (!strcmp(name, "hist_stride_k5")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k5 = (int)value; return PHM_OK; }
+    if (!strcmp(name, "hist_stride_k5")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 (automatic), 1 or 2"); hist_stride_for_k5 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_canonical_swizzle")) { hist_canonical_swizzle = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_tma")) { hist_tma = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_warps_k6")) { PHM_REQUIRE(value == 4 || value == 13, "4 or 13"); hist_warps_k6 = (int)value; return PHM_OK; }
