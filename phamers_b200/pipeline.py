@@ -34,6 +34,7 @@ class ContigScorer(object):
         self.cent_pos = torch.from_numpy(np.ascontiguousarray(centroids[0], dtype=np.float64)).cuda()
         self.cent_neg = torch.from_numpy(np.ascontiguousarray(centroids[1], dtype=np.float64)).cuda()
         self._staging = None
+        self._host_out = None
 
     # -- device resident --------------------------------------------------------------------------------
     def score_device(self, seq, offsets, method="combo", return_counts=True):
@@ -57,10 +58,12 @@ class ContigScorer(object):
         d_seq.copy_(seq_t, non_blocking=True)
         d_off = off_t.to("cuda", non_blocking=True)
         _, scores = self.score_device(d_seq, d_off, method=method, return_counts=False)
-        out = torch.empty(scores.shape, dtype=torch.float64, pin_memory=True)
+        if self._host_out is None or self._host_out.numel() < scores.numel():
+            self._host_out = torch.empty((scores.numel(),), dtype=torch.float64, pin_memory=True)   # pinned once, reused
+        out = self._host_out[:scores.numel()]
         out.copy_(scores, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return out.numpy()
+        return out.numpy().copy()
 
     def score_fasta(self, path, length_requirement=0, method="combo"):
         from . import fileIO
