@@ -80,3 +80,21 @@ def test_host_helpers():
     assert kmer.get_kmer_index("AAAT", "ATGC") == 1          # scripts/kmer.py:90-91
     assert kmer.sequence_to_integers("ATGCNa", "ATGC") == "0123--"
     assert kmer.extend_mers(["A", "T"], 1, "AT") == ["AA", "AT", "TA", "TT"]
+
+
+def test_host_tokeniser_property():
+    """Random files over the bytes that matter to the FASTA tokeniser ('>', line feeds, CR, blanks, tabs, letters): the vectorised
+    host tokeniser agrees with the oracle's line-by-line restatement of the Bio.SeqIO parser on every one of them."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.text(alphabet=">\n\r \tACGTNacgt|_1", min_size=0, max_size=200))
+    def check(text):
+        raw = text.encode("latin-1")
+        ids, seq, off = fileIO.split_fasta_bytes(raw)
+        want = list(po.parse_fasta_text(text))
+        assert ids == [(t.split(None, 1) or [""])[0] for t, _ in want]
+        got = [seq.tobytes().decode("latin-1")[off[i]:off[i + 1]] for i in range(len(ids))]
+        assert got == [s for _, s in want]
+
+    check()

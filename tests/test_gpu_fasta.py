@@ -144,3 +144,16 @@ def test_chunked_upload_of_a_file_larger_than_the_staging_buffers(tmp_path, monk
     h_headers, h_seq, h_off = fileIO.read_fasta_arrays(str(path))
     assert headers == h_headers and np.array_equal(d_off.cpu().numpy(), h_off)
     assert np.array_equal(d_seq.cpu().numpy()[:int(h_off[-1])], h_seq)
+
+
+def test_device_tokeniser_property():
+    """The same property on the device: random files over the bytes that matter ('>', line feeds, CR, blanks, letters; no tab, which
+    the device reports instead of tokenising) against the oracle's restatement of the Bio.SeqIO parser."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.text(alphabet=">\n\r ACGTNacgt|_1", min_size=0, max_size=300))
+    def check(text):
+        _check(text.encode("latin-1"))
+
+    check()
