@@ -289,3 +289,20 @@ def test_tma_staged_histogram_matches_oracle(k):
             assert np.array_equal(_u32(canon), po.canonical_fold(want, k))
     finally:
         _lib.set_option("hist_tma", 0)
+
+
+def test_count_property_small_sequences():
+    """Random short sequences over symbols and non-symbols, through the drop-in kmer.count for k = 1..6, against the oracle's
+    restatement of kmer.count_string (reference scripts/kmer.py:42-50): empty strings, strings shorter than k, blanks at every
+    position relative to the windows and to the 16-byte chunks."""
+    from hypothesis import given, settings, strategies as st
+    from phamers_b200 import kmer
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.text(alphabet="ATGCATGCATGCNatgc-", min_size=0, max_size=90), min_size=2, max_size=12), st.integers(1, 6))
+    def check(seqs, k):
+        got = kmer.count(seqs, k)
+        want = np.stack([po.count_string_np(s, k) for s in seqs])
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+    check()
