@@ -357,3 +357,59 @@ def test_shapes_around_every_tile_boundary():
             assert np.array_equal(np.isnan(got[2]), np.isnan(e[2])), tag
             assert np.max(np.abs(got[1][ok] - e[1][ok]), initial=0.0) <= 1e-12, tag
             assert np.max(np.abs(got[2][ok] - e[2][ok]), initial=0.0) <= 1e-12, tag
+
+
+def test_enlarged_reference_parity(scoring):
+    """BASELINE configs[4] at its full size: 1 M synthetic reference rows (the generator bench.py uses), where the quick reject,
+    the list pass and the 32 M-entry pool actually matter.  2 201 queries, 600 of them sitting exactly on reference rows: the
+    tensor-core path must give the exhaustive float64 kernel's votes and scores (|d| <= 1e-12) without a single row reaching
+    the exhaustive fallback, and the oracle's scores (scikit-learn brute-force kNN over the same 1 M rows, as
+    scripts/learning.py:118-128 calls it) within the stated tolerance with identical signs on a 500-query subset."""
+    import torch
+    from phamers_b200 import kmer, ops, references
+    from tools import workloads
+    g, pos, neg = scoring
+    n_refs = 1000000
+    refs, n_pos = workloads.enlarged_references(pos, neg, n_refs)
+    assert refs.shape == (n_refs, 256) and n_pos == n_refs // 2
+    rng = np.random.default_rng(404)
+    _, pos_c, _, neg_c = references.load_reference_counts()
+    both = np.vstack((pos_c, neg_c)).astype(np.float64)
+    rows = []
+    for _ in range(800):                                                  # contig-like rows: shipped compositions at contig depths
+        src = both[int(rng.integers(0, both.shape[0]))]
+        rows.append(rng.multinomial(int(rng.choice([3000, 16000, 100000])), src / src.sum()))
+    rows.extend(list(rng.integers(0, 120, size=(200, 256))))              # rows far from every reference: long candidate lists
+    rows.append(np.zeros(256, dtype=np.int64))                            # an empty contig -> NaN
+    feats = kmer.normalize_counts(np.stack(rows).astype(np.int64))
+    seq, off = ops.synth_contigs(workloads.SEED, 0, 600)                  # config-2 contigs, counted on the device
+    synth_counts, _ = ops.count_cuda(seq, off, 4)
+    on_refs = refs[torch.from_numpy(rng.choice(n_refs, size=600, replace=False)).cuda()]
+    pts = torch.cat((torch.from_numpy(feats).cuda(), ops.normalize_cuda(synth_counts), on_refs)).contiguous()
+    n = pts.shape[0]
+    assert n >= 2000
+    cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
+    cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
+    try:
+        ops.set_score_path("tc")
+        t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(pts, refs, n_pos, cp, cn, 3)]
+        stats = ops.score_stats()
+        ops.set_score_path("exact")
+        e_knn, e_km, e_combo = [t.cpu().numpy() for t in ops.score_cuda(pts, refs, n_pos, cp, cn, 3)]
+    finally:
+        ops.set_score_path("auto")
+    print("enlarged reference, %d queries x %d rows: %s" % (n, n_refs, stats))
+    assert stats["fallback_rows"] == 0
+    nan_row = len(rows) - 1
+    ok = np.arange(n) != nan_row
+    assert np.isnan(t_combo[nan_row]) and np.isnan(e_combo[nan_row]) and not np.isnan(e_combo[ok]).any()
+    assert np.array_equal(t_knn[ok], e_knn[ok])                           # identical votes
+    assert np.max(np.abs(t_km[ok] - e_km[ok])) <= 1e-12
+    assert np.max(np.abs(t_combo[ok] - e_combo[ok])) <= 1e-12
+    # the oracle on a subset that covers every kind of row (scikit-learn on the host: 500 x 1 M distances)
+    pick = np.concatenate((np.arange(0, 1000, 5), np.arange(1001, 1601, 6), np.arange(1601, n, 3)))[:500]
+    host_refs = refs.cpu().numpy()
+    want = po.score_points(pts[torch.from_numpy(pick).cuda()].cpu().numpy(), host_refs[:n_pos], host_refs[n_pos:],
+                           centroids=(g["centroids_pos"], g["centroids_neg"]))
+    assert np.max(np.abs(t_combo[pick] - want)) <= TOL
+    assert np.array_equal(np.sign(t_combo[pick]), np.sign(want))
