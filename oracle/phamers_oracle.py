@@ -167,6 +167,23 @@ def count_file(input_file, kmer_length, symbols=DNA, normalize=False, fast=False
     return ids, out
 
 
+def count_directory(directory, kmer_length, identifier="fna", symbols=DNA, sum_file=True, fast=True):
+    """scripts/kmer.py:143-180 (live behaviour, sample = 0): the files of `directory` whose basename contains `identifier`, in
+    os.listdir order; with sum_file one row per file -- the id of its first record (:171) and the sum of its records' counts
+    (:172) -- as float64 (:159); files that cannot be read or hold no window are dropped (:165-168).  (sum_file = False leaves
+    file_id unset in the reference, :170-175, and is not restated.)"""
+    import os
+    selected = [os.path.join(directory, f) for f in os.listdir(directory) if identifier in os.path.basename(f)]
+    ids, rows = [], []
+    for path in selected:
+        file_ids, file_counts = count_file(path, kmer_length, symbols=symbols, fast=fast)
+        if file_ids is None or len(file_ids) == 0 or np.sum(file_counts) == 0:
+            continue
+        ids.append(file_ids[0])
+        rows.append(np.sum(file_counts, axis=0) if file_counts.ndim == 2 else file_counts)
+    return ids, (np.array(rows, dtype=float) if rows else np.zeros((0, len(symbols) ** kmer_length)))
+
+
 # ---- canonical (reverse-complement) folding: north-star extension, no reference code ----
 def revcomp_index(j, k):
     """Bin of the reverse complement of bin j in ATGC order (A<->T is 0<->1, G<->C is 2<->3)."""

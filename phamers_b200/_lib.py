@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "lib", "libphamers_b200.so")
+# PHAMERS_B200_LIB: another build of the same library (tuning experiments only; it must export the same C-ABI)
+_PATH = os.environ.get("PHAMERS_B200_LIB") or os.path.join(_HERE, "lib", "libphamers_b200.so")
 _lib = None
 
 PHM_COUNT_CANONICAL = 1

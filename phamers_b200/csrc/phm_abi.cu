@@ -41,6 +41,7 @@ extern int hist_stride_for_k5;
 extern int hist_warps_k6;
 extern int hist_tma;
 extern int hist_canonical_swizzle;
+extern int hist_plan;
 extern int score_path;
 extern int score_collect_stats;
 extern int score_list_pass;
@@ -80,6 +81,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_stride_k4")) { PHM_REQUIRE(value == 1 || value == 2, "1 or 2"); hist_stride_for_k4 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_stride_k5")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 (automatic), 1 or 2"); hist_stride_for_k5 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_canonical_swizzle")) { hist_canonical_swizzle = value != 0; return PHM_OK; }
+    if (!strcmp(name, "hist_plan")) { hist_plan = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_tma")) { hist_tma = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_warps_k6")) { PHM_REQUIRE(value == 4 || value == 13, "4 or 13"); hist_warps_k6 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 0 && value <= 4096, "0 (automatic) .. 4096"); hist_contigs_per_item = (int)value; return PHM_OK; }

@@ -17,10 +17,12 @@ using namespace phm;
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// layout: the scorer's workspace first (its size follows from the shapes), then the counting workspace, which takes whatever is left --
+// its list of long work items is sized by the number of BASES, which this entry point is not told (see phm_kmer_count_workspace_bytes)
 extern "C" size_t phm_count_score_workspace_bytes(int64_t n_contigs, int64_t n_bases, int64_t n_refs, int64_t n_cent_pos,
                                                   int64_t n_cent_neg) {
-    return align256(phm_kmer_count_workspace_bytes(n_contigs, n_bases, 4, 0)) +
-           phm_score_workspace_bytes(n_contigs, n_refs, n_cent_pos, n_cent_neg, 256);
+    return align256(phm_score_workspace_bytes(n_contigs, n_refs, n_cent_pos, n_cent_neg, 256)) +
+           phm_kmer_count_workspace_bytes(n_contigs, n_bases, 4, 0);
 }
 
 extern "C" int phm_count_score(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_contigs,
@@ -38,14 +40,14 @@ extern "C" int phm_count_score(const uint8_t *d_seq, const int64_t *d_offsets, i
         set_error("phm_count_score needs the tensor-core shape: k_neighbors in {1, 3, 5} <= n_refs and both centroid sets");
         return PHM_E_UNSUPPORTED;
     }
-    const size_t count_ws = align256(phm_kmer_count_workspace_bytes(n_contigs, 0, 4, 0));
+    const size_t score_ws_bytes = align256(phm_score_workspace_bytes(n_contigs, n_refs, n_cent_pos, n_cent_neg, 256));
     if (workspace_bytes < phm_count_score_workspace_bytes(n_contigs, 0, n_refs, n_cent_pos, n_cent_neg)) {
         set_error("workspace too small");
         return PHM_E_WORKSPACE;
     }
-    unsigned char *ws = static_cast<unsigned char *>(d_workspace);
-    void *score_ws = ws + count_ws;
-    const size_t score_ws_bytes = workspace_bytes - count_ws;
+    unsigned char *score_ws = static_cast<unsigned char *>(d_workspace);
+    void *ws = score_ws + score_ws_bytes;
+    const size_t count_ws = workspace_bytes - score_ws_bytes;
 
     ScoreArgs a;
     a.points = nullptr; a.point_counts = d_counts; a.n_points = n_contigs; a.dim = 256;

@@ -57,6 +57,36 @@ __device__ __forceinline__ __half prep_accumulate(double x, double &s, double &s
     sh = fma(hv, hv, sh);
     return h;
 }
+// Sums of four doubles over the warp with 16 shuffles instead of 40: a butterfly that TRANSPOSES while it reduces (after the first
+// exchange a lane carries two of the four values, after the second one), then three plain steps.  Every value is still reduced by
+// the tree xor 16, 8, 4, 2, 1, so the sums have the bits the plain butterfly gives.  The results are valid in LANE 0 only.
+__device__ __forceinline__ void warp_sum4(double &a, double &b, double &c, double &d, int lane) {
+    const bool up = (lane & 16) != 0;
+    const double k0 = (up ? c : a) + __shfl_xor_sync(FULL, up ? a : c, 16);
+    const double k1 = (up ? d : b) + __shfl_xor_sync(FULL, up ? b : d, 16);
+    const bool up2 = (lane & 8) != 0;
+    double k = (up2 ? k1 : k0) + __shfl_xor_sync(FULL, up2 ? k0 : k1, 8);
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    a = k;                                          // lane 0 holds a, lane 8 b, lane 16 c, lane 24 d
+    b = __shfl_sync(FULL, k, 8);
+    c = __shfl_sync(FULL, k, 16);
+    d = __shfl_sync(FULL, k, 24);
+}
+__device__ __forceinline__ void warp_sum3(double &a, double &b, double &c, int lane) {
+    const bool up = (lane & 16) != 0;
+    const double k0 = (up ? c : a) + __shfl_xor_sync(FULL, up ? a : c, 16);
+    const double k1 = (up ? 0.0 : b) + __shfl_xor_sync(FULL, up ? b : 0.0, 16);
+    const bool up2 = (lane & 8) != 0;
+    double k = (up2 ? k1 : k0) + __shfl_xor_sync(FULL, up2 ? k0 : k1, 8);
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    a = k;
+    b = __shfl_sync(FULL, k, 8);
+    c = __shfl_sync(FULL, k, 16);
+}
 // err_j <= dA P_j + nA dB_j + eps_acc nA |B_j| + (FP32 roundings of nbs_j, of nbs_j - acc_j and of the fma)
 //       <= P_j (dA + nA rho + 2^-21 (pmax + nA))        then 1 % on top for the FP32 arithmetic on the bounds
 __device__ __forceinline__ float query_crow(double sc, double sd, double sh, float rho, float pmax) {

@@ -712,13 +712,7 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
                                      : r * KDIM + d;
             op[o] = prep_accumulate(x, s, sc, sd, sh);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(FULL, s, o);
-            sc += __shfl_xor_sync(FULL, sc, o);
-            sd += __shfl_xor_sync(FULL, sd, o);
-            sh += __shfl_xor_sync(FULL, sh, o);
-        }
+        warp_sum4(s, sc, sd, sh, lane);                    // valid in lane 0
         if (lane == 0) {
             const bool real = r < n_src;
             if (norm64 && real) norm64[sr] = s;

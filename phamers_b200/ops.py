@@ -183,9 +183,6 @@ def score_stats():
     true ranking values use (must stay <= 1) and the largest ranking error in squared-distance units."""
     lib = _lib.require_cuda()
     ws = _workspaces[(_last_score_ws[0], torch.cuda.current_device())]
-    if _last_score_ws[0] == "count_score":           # the scorer's share starts after the (256-byte aligned) count workspace
-        skip = (lib.phm_kmer_count_workspace_bytes(0, 0, 4, 0) + 255) // 256 * 256
-        ws = ws[skip:]
     rows, err = ctypes.c_uint64(0), (ctypes.c_float * 4)()
     check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
     return {"fallback_rows": int(rows.value), "max_bound_usage": float(err[0]), "max_rank_error": float(err[1]),

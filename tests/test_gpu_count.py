@@ -306,3 +306,128 @@ def test_count_property_small_sequences():
         assert got.shape == want.shape and np.array_equal(got, want)
 
     check()
+
+
+def _long_workload(rng):
+    """Records of genome size next to contig-size ones: a 16 Mbp record (cut into ~250 tiles), records just below / at / above the
+    listing and splitting thresholds (16 384 / 131 072 bases), tile boundaries that fall on and next to blank bytes."""
+    lengths = np.array([5000, 16 * 1024 * 1024 + 77, 16383, 16384, 131071, 131072, 131073, 3, 0, 262144 + 511, 65536 * 3 + 1, 40000,
+                        1000000, 17, 196608], dtype=np.int64)
+    off = np.concatenate(([0], np.cumsum(lengths)))
+    seq = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(off[-1]), p=[0.35, 0.33, 0.15, 0.17])
+    big = int(off[1])
+    for t in range(1, 40):                                              # blanks on, just before and just after tile boundaries
+        edge = ((big + t * 65536) // 512) * 512
+        seq[edge + int(rng.integers(-6, 7))] = ord("N")
+    seq[big + 3000000:big + 3000300] = ord("n")                        # a soft-masked stretch
+    seq[int(off[12]):int(off[12]) + 400000] = ord("G")                  # a homopolymer run across tiles: one bin takes every count
+    return seq, off
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 2])
+def test_long_records_are_tiled_bit_exact(k):
+    """SURVEY.md section 5 (long records: kmer.count_directory runs over whole genomes, scripts/kmer.py:143-180): a record of
+    131 072 bases or more is cut into 64 kb tiles counted by different warps and merged in its output row; counts, canonical
+    counts and features must still be the oracle's, bit for bit, whatever outputs are asked for."""
+    from phamers_b200 import ops, _lib
+    rng = np.random.default_rng(160 + k)
+    seq, off = _long_workload(rng)
+    d_seq, d_off = _device(seq, off)
+    want = c_oracle.count(seq, off, k)
+    counts, freq = ops.count_cuda(d_seq, d_off, k, freq=True)
+    assert np.array_equal(_u32(counts), want)
+    assert np.array_equal(freq.cpu().numpy(), c_oracle.normalize(want), equal_nan=True)
+    _, only_freq = ops.count_cuda(d_seq, d_off, k, counts=False, freq=True)            # tiles merge inside the feature rows
+    assert torch.equal(only_freq, freq) or np.array_equal(only_freq.cpu().numpy(), freq.cpu().numpy(), equal_nan=True)
+    want_c = po.canonical_fold(want, k)
+    canon, cfreq = ops.count_cuda(d_seq, d_off, k, canonical=True, freq=True)
+    assert np.array_equal(_u32(canon), want_c)
+    assert np.array_equal(cfreq.cpu().numpy(), c_oracle.normalize(want_c), equal_nan=True)
+    _, only_cfreq = ops.count_cuda(d_seq, d_off, k, canonical=True, counts=False, freq=True)
+    assert np.array_equal(only_cfreq.cpu().numpy(), cfreq.cpu().numpy(), equal_nan=True)
+    # the same without the work plan (every record one work item, as in round 1) and with a workspace too small for the list
+    _lib.set_option("hist_plan", 0)
+    try:
+        plain, _ = ops.count_cuda(d_seq, d_off, k)
+    finally:
+        _lib.set_option("hist_plan", 1)
+    assert torch.equal(plain, counts)
+    lib = _lib.load()
+    small = torch.empty((int(lib.phm_kmer_count_workspace_bytes(len(off) - 1, 0, k, 0)),), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(counts)
+    _lib.check(lib.phm_kmer_count(_lib.ptr(d_seq), _lib.ptr(d_off), len(off) - 1, k, 0, _lib.ptr(out), None, _lib.ptr(small),
+                                  small.numel(), _lib.stream_ptr()))
+    assert torch.equal(out, counts)
+
+
+def test_long_record_is_counted_in_parallel():
+    """One 16 Mbp record on its own: ~250 tiles on as many warps.  Device time must be far below the ~30 ms a single warp needs."""
+    from phamers_b200 import ops
+    rng = np.random.default_rng(16)
+    n = 16 * 1024 * 1024
+    seq = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=n)
+    off = np.array([0, n], dtype=np.int64)
+    d_seq, d_off = _device(seq, off)
+    counts, _ = ops.count_cuda(d_seq, d_off, 4)
+    assert np.array_equal(_u32(counts), c_oracle.count(seq, off, 4))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.count_cuda(d_seq, d_off, 4, out_counts=counts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("16 Mbp record: %.3f ms per count" % ms)
+    assert ms < 1.0
+
+
+def test_count_score_with_long_records(tmp_path):
+    """The fused path (histogram kernel emitting the scorer's operands) on a workload with tiled records: same counts and the
+    same scores as counting first and scoring the counts."""
+    from phamers_b200 import ops, pipeline
+    rng = np.random.default_rng(99)
+    lengths = np.array([20000, 300000, 1000, 140000, 5000, 9000, 131072, 70000], dtype=np.int64)
+    off = np.concatenate(([0], np.cumsum(lengths)))
+    seq = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=int(off[-1]), p=[0.3, 0.3, 0.2, 0.2])
+    seq[int(off[1]) + 65536 * 2] = ord("N")
+    d_seq, d_off = _device(seq, off)
+    scorer = pipeline.ContigScorer()
+    counts, combo = scorer.score_device(d_seq, d_off)
+    want = c_oracle.count(seq, off, 4)
+    assert np.array_equal(_u32(counts), want)
+    plain, _ = ops.count_cuda(d_seq, d_off, 4)
+    _, _, combo2 = ops.score_cuda(plain, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)
+    assert torch.equal(combo, combo2)
+
+
+def test_count_directory_of_genome_files(tmp_path):
+    """kmer.count_directory (reference scripts/kmer.py:143-180) over a directory of genome files -- how the reference builds its
+    reference feature sets: a 10-record genome (records of 0.1 - 2.2 Mbp, 70-column lines), a single-chromosome file, a gzipped
+    file, a file without usable sequence (dropped) and a file the identifier does not select."""
+    import gzip
+    from phamers_b200 import kmer
+    rng = np.random.default_rng(2024)
+
+    def record(name, length, gc):
+        p = [(1 - gc) / 2, (1 - gc) / 2, gc / 2, gc / 2]
+        s = rng.choice(np.frombuffer(b"ATGC", dtype=np.uint8), size=length, p=p)
+        if length > 1000:
+            s[length // 2:length // 2 + 40] = ord("N")
+        text = s.tobytes().decode("ascii")
+        return ">%s some description\n" % name + "\n".join(text[i:i + 70] for i in range(0, length, 70)) + "\n"
+
+    genome = "".join(record("NC_%06d.1" % i, int(L), 0.3 + 0.04 * i) for i, L in
+                     enumerate([2200000, 100000, 131072, 1500000, 400000, 65536, 180000, 1000000, 131071, 700000]))
+    (tmp_path / "genome_a.fna").write_text(genome)
+    (tmp_path / "genome_b.fna").write_text(record("NZ_CP000001.1", 3000001, 0.62))
+    with gzip.open(str(tmp_path / "genome_c.fna.gz"), "wt") as fh:
+        fh.write(record("NZ_CP000002.1", 250000, 0.5) + record("NZ_CP000003.1", 3, 0.5))
+    (tmp_path / "empty.fna").write_text(">nothing\nNNNN\n")
+    (tmp_path / "notes.txt").write_text(">ignored\nATGCATGC\n")
+    for k in (4, 6):
+        ids, counts = kmer.count_directory(str(tmp_path), k)
+        want_ids, want = po.count_directory(str(tmp_path), k)
+        assert list(ids) == list(want_ids) and len(ids) == 3
+        assert counts.dtype == np.float64 and counts.shape == want.shape
+        assert np.array_equal(counts, want)
