@@ -8,11 +8,18 @@
  *
  * Conventions
  *   - extern "C", plain pointers and sizes only.  Every `d_*` pointer is a DEVICE pointer on the
- *     current CUDA device, every `h_*` pointer is a HOST pointer (pinned memory recommended).
+ *     current CUDA device; `h_*` marks the few HOST pointers (small result blocks).
  *   - All launches go to `stream` (a cudaStream_t / CUstream passed as void*; NULL = default stream).
- *     Device entry points never allocate and never synchronise; scratch memory is caller-owned
- *     (`d_workspace`, sized by the matching *_workspace_bytes function).  Host-buffer entry points
- *     (phm_*_host) own a lazily created staging pool and return after the result is in host memory.
+ *     Entry points never allocate; scratch memory is caller-owned (`d_workspace`, sized by the matching
+ *     *_workspace_bytes function) and they do not synchronise unless their comment says so.
+ *   - Concurrency: calls that use DIFFERENT workspaces may run concurrently on different streams, threads
+ *     and devices.  A workspace holds live kernel state (work counters, candidate lists), so two calls
+ *     must never share one while either is in flight.  The tuning options of phm_set_option and the
+ *     timing hooks (phm_last_kernel_ms, phm_kernel_launches) are PROCESS-WIDE and not synchronised: set
+ *     them while no call is running.
+ *   - Sequence buffers (`d_seq`, `d_raw`) are read with 128-bit loads: they must be 16-byte aligned and
+ *     the allocation must be READABLE up to the next multiple of 16 bytes past the last base (the
+ *     content of that padding does not matter).
  *   - Return value: 0 = ok, negative = error (PHM_E_*); phm_last_error() gives the message of the
  *     most recent failure on the calling thread.
  *   - Bin order everywhere is the reference's: symbols 'ATGC' (A=0 T=1 G=2 C=3), first base most
@@ -78,7 +85,10 @@ int phm_pack_fasta(const uint8_t *d_seq, int64_t n_bases, uint32_t *d_codes, uin
  *     d_counts   uint32[n_contigs * bins]          (may be NULL)  -- bit-exact with the reference.
  *     d_freq     float64[n_contigs * bins]         (may be NULL)  -- counts / row sum, IEEE division
  *                exactly as numpy does it; an all-zero row gives NaN like kmer.py:219-220.
- *     d_workspace / workspace_bytes  scratch from phm_kmer_count_workspace_bytes().
+ *     d_workspace / workspace_bytes  scratch from phm_kmer_count_workspace_bytes(n_contigs, n_bases, ...).  Its size grows with
+ *                n_bases because it holds the list of work items of records that are cut into tiles (131 072 bases and more are
+ *                counted by many warps and merged).  A workspace sized for fewer bases than the offsets describe is legal: such
+ *                records are then counted whole by one warp each.
  * ------------------------------------------------------------------------------------------- */
 size_t phm_kmer_count_workspace_bytes(int64_t n_contigs, int64_t n_bases, int k, uint32_t flags);
 int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, int64_t n_contigs, int k, uint32_t flags,
@@ -92,6 +102,10 @@ int phm_kmer_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, cons
 
 /* kmer.normalize_counts on its own (scripts/kmer.py:209-221) for counts that are already on the device. */
 int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, int64_t bins, double *d_freq, void *stream);
+/* The same for rows that are not exact 32-bit counts (the summed genome counts of kmer.count_directory, already-float features):
+ * float64 row / row sum.  Equals numpy's result for integer-valued rows with sums below 2^53; otherwise the row sum may differ
+ * from numpy's pairwise sum in the last bit. */
+int phm_normalize_rows(const double *d_rows, int64_t n_rows, int64_t bins, double *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4+K5  scoring.  Replaces phamer_scorer.knn_score_points / kmeans_score_points / combo_score_points
@@ -132,6 +146,10 @@ int phm_score_counts(const uint32_t *d_counts, int64_t n_points, int dim,
                      const double *d_cent_pos, int64_t n_cent_pos, const double *d_cent_neg, int64_t n_cent_neg,
                      int k_neighbors, double *d_knn, double *d_kmeans, double *d_combo,
                      void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* learning.distances (scripts/learning.py:47-56): Euclidean distance, float64 by direct difference, of d_point[dim] to each of
+ * d_rows[n_rows * dim] -> d_out[n_rows].  learning.closest_to (:59-66) is the row with the first smallest of them. */
+int phm_distances(const double *d_point, const double *d_rows, int64_t n_rows, int dim, double *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The whole hot path in one call (k = 4): count -> normalise -> score with the reference's default 'combo' method, i.e. what
@@ -192,13 +210,19 @@ int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max
 
 /* Tuning / path selection for experiments and tests (defaults are the measured best; every variant gives the same results).
  * Options: "hist_stride_k4" (2 | 1: 5-mer windows at every second base | plain 4-mers), "hist_stride_k5" (0 = automatic | 1 | 2: 6-mer windows in 16-bit packed counters),
- * "hist_warps_k6" (13 | 4), "hist_contigs_per_item" (0 = automatic), "hist_canonical_swizzle" (1 | 0: bank-swizzled table for the
- * canonical fold at k = 5, 6), "hist_tma" (0 | 1: sequence staged in shared memory by cp.async.bulk),
+ * "hist_warps_k6" (13 | 4), "hist_canonical_swizzle" (1 | 0: bank-swizzled table for the canonical fold at k = 5, 6),
+ * "hist_tma" (0 | 1: sequence staged in shared memory by cp.async.bulk), "hist_plan" (1 | 0: records of 131 072 bases and more
+ * are cut into tiles counted by different warps | every record is one work item),
+ * "score_force_fallback" (1 = the first tensor-core pass keeps no candidate, so that every row takes the overflow road -- listing pass
+ * or exhaustive kernels; this is how the tests exercise those kernels),
  * "score_list_pass" (0 = overflowed rows skip the listing pass and go to the exhaustive kernels),
  * "score_path" (0 = tensor cores when the shape allows, 1 = exhaustive float64 only, 2 = tensor cores or error),
  * "score_stats" (1 = collect error-interval diagnostics, slower), "time_kernels" (1 = bracket the hot kernels with CUDA
  * events for phm_last_kernel_ms). */
 int phm_set_option(const char *name, int64_t value);
+
+/* Kernels this library has launched in the calling process so far (bench.py reports the difference over its timed region). */
+uint64_t phm_kernel_launches(void);
 
 /* Mean device time (ms) of the launches (at most 64) of a hot kernel ("kmer_hist_kernel", "score_tc_kernel") since the previous
  * call for that kernel; needs option "time_kernels" = 1 before the launches.  Synchronises on the last of them. */

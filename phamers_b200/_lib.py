@@ -27,6 +27,9 @@ SIGNATURES = {
     "phm_kmer_count_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_uint32, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
     "phm_normalize_counts": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "phm_normalize_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "phm_distances": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "phm_kernel_launches": (c_uint64, []),
     "phm_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "phm_score": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                           c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -69,6 +72,7 @@ def load():
     if not os.path.exists(_PATH):
         raise PhamersLibraryError(
             "%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; there is no CPU fallback" % _PATH)
+    import torch  # noqa: F401  (brings the CUDA runtime shared object into the process; the library links against it)
     lib = ctypes.CDLL(_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         try:

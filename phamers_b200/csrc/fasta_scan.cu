@@ -427,10 +427,10 @@ extern "C" int phm_fasta_index(const uint8_t *d_raw, int64_t n_bytes, int64_t *d
         int64_t grid = (int64_t)sm_count() * 8;
         if (grid > n_tiles) grid = n_tiles;
         fasta::fasta_tile_kernel<<<(unsigned)grid, fasta::TILE_THREADS, 0, st>>>(d_raw, n_bytes, n_tiles, w.tiles);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
     }
     fasta::fasta_chain_kernel<<<1, 1024, 0, st>>>(w.tiles, n_tiles, w.starts, d_result);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -450,6 +450,6 @@ extern "C" int phm_fasta_extract(const uint8_t *d_raw, int64_t n_bytes, const in
     if (grid < 1) grid = 1;
     fasta::fasta_emit_kernel<<<(unsigned)grid, fasta::TILE_THREADS, 0, st>>>(d_raw, n_bytes, n_tiles, w.starts, d_result, d_seq, d_offsets,
                                                                              d_header_pos, max_records);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }

@@ -144,7 +144,7 @@ extern "C" int phm_kmeans_lloyd(const double *d_x, int64_t n, int dim, double *d
         else if (per_lane <= 16) PHM_KM_ASSIGN(16);
         else PHM_KM_ASSIGN(32);
 #undef PHM_KM_ASSIGN
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
         return PHM_OK;
     };
     h_info[0] = 0; h_info[1] = 0; h_info[2] = 0;
@@ -153,7 +153,7 @@ extern "C" int phm_kmeans_lloyd(const double *d_x, int64_t n, int dim, double *d
         PHM_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(km::Control), st));
         if ((rc = assign()) != PHM_OK) return rc;                                                   // E step with the current centres
         km::update_kernel<<<(unsigned)k, 256, 0, st>>>(d_x, n, dim, d_labels, d_centres, k, &ctl->shift2, &ctl->empty);   // M step
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
         km::Control h;
         PHM_CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
         PHM_CUDA_CHECK(cudaStreamSynchronize(st));

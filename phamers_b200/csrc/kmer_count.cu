@@ -983,8 +983,6 @@ static EventRing g_hist_ring;        // brackets of the kmer_hist_kernel launche
 int kmer_hist_last_ms(float *ms) { return g_hist_ring.mean_ms(ms); }
 
 int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
-int hist_contigs_per_item = 0;          // contigs a warp takes per visit to the work counter; 0 = 1 for k <= 5 (finest balance: 5.03 vs 5.10 ms at
-                                        // k = 4), 4 for k = 6 (12.5 vs 12.8 ms)
 int hist_stride_for_k5 = 0;          // 0 = automatic: 6-mers at every second base in 16-bit packed counters for plain bins (7.96 vs 8.22 ms),
                                      // plain 5-mers on the bank-swizzled table for canonical bins (7.70 vs 8.90 ms); 1 | 2 force one
 int hist_warps_k6 = 13;
@@ -999,9 +997,9 @@ static int launch_plan(const int64_t *off, int64_t n, int k, const CountWorkspac
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     hist_plan_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(off, n, w.plan);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     hist_plan_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(off, n, k, w.plan, w.entries, w.cap, counts, freq, out_bins);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -1032,10 +1030,10 @@ static int launch_hist(const uint8_t *seq, const int64_t *off, int64_t n, uint32
     const int64_t need = (items + WARPS - 1) / WARPS;
     if (grid > need) grid = need < 1 ? 1 : need;
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(job, emit);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     if (job.cap > 0) {
         hist_finish_kernel<EMIT><<<sm_count(), 256, 0, st>>>(job, emit);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
     }
     if (timed) g_hist_ring.end(st);
     return PHM_OK;
@@ -1057,12 +1055,12 @@ static int launch_hist_packed(const uint32_t *codes, const uint32_t *valid, cons
     PHM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) { set_error("packed histogram kernel does not fit on an SM (smem %zu)", smem); return PHM_E_UNSUPPORTED; }
     int64_t grid = (int64_t)per_sm * sm_count();
-    const int per_item = hist_contigs_per_item > 0 ? hist_contigs_per_item : 4;
+    const int per_item = 4;
     const int64_t items = (n + per_item - 1) / per_item;
     const int64_t need = (items + WARPS - 1) / WARPS;
     if (grid > need) grid = need < 1 ? 1 : need;
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(codes, valid, off, n, counts, freq, rc, compact, out_bins, counter, per_item);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -1115,7 +1113,7 @@ static int prepare_count(int64_t n_contigs, int k, uint32_t flags, void *ws, siz
     *out_bins = 1 << (2 * k);
     if (flags & PHM_COUNT_CANONICAL) {
         canonical_lut_kernel<<<1, 1024, 0, st>>>(k, w->rc_lut, w->compact_lut, w->canon_lut);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
         *rc = w->rc_lut; *compact = w->compact_lut;
         *out_bins = (int)canonical_bins(k);
     }
@@ -1140,7 +1138,7 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
         int64_t blocks = (n_contigs + 7) / 8;
         if (blocks > 148 * 16) blocks = 148 * 16;
         kmer_naive_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_seq, d_offsets, n_contigs, k, d_counts, rc, compact, out_bins);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
         if (d_freq) return phm_normalize_counts(d_counts, n_contigs, out_bins, d_freq, stream);
         return PHM_OK;
     }
@@ -1201,7 +1199,7 @@ extern "C" int phm_normalize_counts(const uint32_t *d_counts, int64_t n_rows, in
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     normalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_counts, n_rows, bins, d_freq);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -1215,6 +1213,6 @@ extern "C" int phm_pack_fasta(const uint8_t *d_seq, int64_t n_bases, uint32_t *d
     const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     pack_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_seq, n_bases, d_codes, d_valid);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }

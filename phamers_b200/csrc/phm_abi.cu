@@ -16,27 +16,38 @@ void set_error(const char *fmt, ...) {
 
 int time_kernels = 0;
 
-static int g_sm_count = 0, g_smem_optin = 0;
+unsigned long long kernel_launches = 0;
 
-static void query_device() {
+// device attributes, cached per device ordinal (a process may drive several GPUs from several threads)
+static constexpr int kMaxDevices = 64;
+static int g_sm_count[kMaxDevices], g_smem_optin[kMaxDevices];
+
+static int current_device() {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
 int sm_count() {
-    if (g_sm_count == 0) query_device();
-    return g_sm_count;
+    const int dev = current_device();
+    if (g_sm_count[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        g_sm_count[dev] = v > 0 ? v : 148;
+    }
+    return g_sm_count[dev];
 }
 int max_smem_optin() {
-    if (g_smem_optin == 0) query_device();
-    return g_smem_optin;
+    const int dev = current_device();
+    if (g_smem_optin[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        g_smem_optin[dev] = v;
+    }
+    return g_smem_optin[dev];
 }
 
 extern int hist_stride_for_k4;
-extern int hist_contigs_per_item;
 extern int hist_stride_for_k5;
 extern int hist_warps_k6;
 extern int hist_tma;
@@ -45,7 +56,7 @@ extern int hist_plan;
 extern int score_path;
 extern int score_collect_stats;
 extern int score_list_pass;
-extern int score_debug;
+extern int score_force_fallback;
 int kmer_hist_last_ms(float *ms);
 
 }  // namespace phm
@@ -84,15 +95,16 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_plan")) { hist_plan = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_tma")) { hist_tma = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_warps_k6")) { PHM_REQUIRE(value == 4 || value == 13, "4 or 13"); hist_warps_k6 = (int)value; return PHM_OK; }
-    if (!strcmp(name, "hist_contigs_per_item")) { PHM_REQUIRE(value >= 0 && value <= 4096, "0 (automatic) .. 4096"); hist_contigs_per_item = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_path")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 auto, 1 exact, 2 tensor cores"); score_path = (int)value; return PHM_OK; }
     if (!strcmp(name, "time_kernels")) { time_kernels = value != 0; return PHM_OK; }
-    if (!strcmp(name, "score_debug")) { score_debug = (int)value; return PHM_OK; }
+    if (!strcmp(name, "score_force_fallback")) { score_force_fallback = value != 0; return PHM_OK; }
     if (!strcmp(name, "score_stats")) { score_collect_stats = value != 0; return PHM_OK; }
     if (!strcmp(name, "score_list_pass")) { score_list_pass = value != 0; return PHM_OK; }
     set_error("unknown option '%s'", name);
     return PHM_E_ARG;
 }
+
+extern "C" uint64_t phm_kernel_launches(void) { return (uint64_t)kernel_launches; }
 
 // Device time of the most recent launch of a named hot kernel (bench.py's roofline numerator); synchronises on that launch.
 extern "C" int phm_last_kernel_ms(const char *kernel, float *ms) {

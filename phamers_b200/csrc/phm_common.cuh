@@ -28,8 +28,16 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
-int sm_count();                       // cached multiprocessor count of the current device
-int max_smem_optin();                 // cached opt-in shared memory per block
+int sm_count();                       // multiprocessor count of the CURRENT device (cached per device)
+int max_smem_optin();                 // opt-in shared memory per block of the current device (cached per device)
+
+extern unsigned long long kernel_launches;      // kernels this library has launched in this process (phm_kernel_launches)
+// after every <<< >>>: counts the launch and turns a launch error into PHM_E_CUDA
+#define PHM_LAUNCH_CHECK()                                                                     \
+    do {                                                                                       \
+        ++phm::kernel_launches;                                                                \
+        PHM_CUDA_CHECK(cudaGetLastError());                                                    \
+    } while (0)
 
 extern int time_kernels;              // option "time_kernels": hot kernels are bracketed with CUDA events (phm_last_kernel_ms)
 

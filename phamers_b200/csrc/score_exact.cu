@@ -193,7 +193,7 @@ int launch_score_exact(const ScoreArgs &a, cudaStream_t st) {
     const int64_t blocks = (a.n_rows + TQ - 1) / TQ;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(score_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExactSmem)));
     score_exact_kernel<<<(unsigned)blocks, 256, sizeof(ExactSmem), st>>>(a);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -202,8 +202,43 @@ int launch_row_norms(const double *x, int64_t n_rows, int dim, double *out, cuda
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     row_norms_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n_rows, dim, out);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
+}
+
+// learning.distances (scripts/learning.py:47-56): Euclidean distance of one point to every row, float64 by direct difference
+// (the arithmetic every exact path of the scorer uses).  One warp per row.
+__global__ void __launch_bounds__(256) distances_kernel(const double *__restrict__ point, const double *__restrict__ rows, int64_t n_rows,
+                                                        int dim, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        double acc = 0.0;
+        for (int d = lane; d < dim; d += 32) {
+            const double t = point[d] - rows[r * dim + d];
+            acc = fma(t, t, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == 0) out[r] = sqrt(acc);
+    }
+}
+
+// kmer.normalize_counts for rows that are not exact 32-bit counts (summed genome counts, features): row / row sum in float64.
+// The row sum is accumulated in float64 lane by lane and then across the warp; for integer-valued rows below 2^53 it is exact
+// and the result equals numpy's, for other rows it can differ from numpy's pairwise sum in the last bit.
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const double *__restrict__ in, int64_t n_rows, int64_t bins, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        double total = 0.0;
+        for (int64_t b = lane; b < bins; b += 32) total += in[r * bins + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+        for (int64_t b = lane; b < bins; b += 32) out[r * bins + b] = in[r * bins + b] / total;
+    }
 }
 
 }  // namespace phm
@@ -297,4 +332,26 @@ extern "C" int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows,
     int rc = tc::score_tc_stats(d_workspace, &fb, max_rank_error, static_cast<cudaStream_t>(stream));
     *fallback_rows = fb;
     return rc;
+}
+
+extern "C" int phm_distances(const double *d_point, const double *d_rows, int64_t n_rows, int dim, double *d_out, void *stream) {
+    PHM_REQUIRE(n_rows >= 0 && dim > 0, "bad shape");
+    if (n_rows == 0) return PHM_OK;
+    PHM_REQUIRE(d_point != nullptr && d_rows != nullptr && d_out != nullptr, "null pointer");
+    int64_t blocks = (n_rows + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    distances_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_point, d_rows, n_rows, dim, d_out);
+    PHM_LAUNCH_CHECK();
+    return PHM_OK;
+}
+
+extern "C" int phm_normalize_rows(const double *d_rows, int64_t n_rows, int64_t bins, double *d_out, void *stream) {
+    PHM_REQUIRE(n_rows >= 0 && bins > 0, "bad shape");
+    if (n_rows == 0) return PHM_OK;
+    PHM_REQUIRE(d_rows != nullptr && d_out != nullptr, "null pointer");
+    int64_t blocks = (n_rows + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_rows, n_rows, bins, d_out);
+    PHM_LAUNCH_CHECK();
+    return PHM_OK;
 }

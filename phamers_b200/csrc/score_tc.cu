@@ -43,7 +43,8 @@
 
 namespace phm {
 
-int score_debug = 0;              // option "score_debug": timing experiments only (1 = epilogue skips the scan, 2 = scan without hits)
+int score_force_fallback = 0;     // option "score_force_fallback": the first pass keeps no candidate, so every row takes the overflow road
+                                  // (list pass, or the exhaustive kernels when that is off) -- how the tests reach those kernels
 int score_collect_stats = 0;      // option "score_stats": re-measure every candidate and record how much of the bound is used
 int score_list_pass = 1;          // option "score_list_pass": 0 = overflowed rows go straight to the exhaustive kernels
 
@@ -407,7 +408,7 @@ struct TcParams {
     uint2 *cand;                         // [n_points, 16] (lower bound as float bits, column within its class)
     float *cand_up;                      // [n_points, 16] matching upper bounds (lower + 2 C P)
     int ref_pad, cp_pad;                 // offsets of the centroid classes in nbs / pnorm
-    int debug;                           // timing experiments: 1 = no scan, 2 = no hit processing
+    int skip_scan;                       // option score_force_fallback: the epilogue keeps nothing
     uint32_t *meta;                      // [n_points] cnt_ref | cnt_pos << 8 | cnt_neg << 16 | flags << 24 (1 = centroid overflow)
     float2 *drop_lo;                     // [n_points] smallest lower bound of a dropped negative (.x) / positive (.y) reference
     float *thr_out;                      // [n_points] the row's final threshold: k-th smallest upper bound over every reference seen, kept or dropped
@@ -562,7 +563,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
         for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
             const int mt = item / sched.n_slices;
             const int64_t row = (int64_t)mt * MT + row_in_tile;
-            float C = (row < sched.n_rows && p.debug != 2) ? p.crow[row] : NAN;
+            float C = (row < sched.n_rows) ? p.crow[row] : NAN;
             const bool live = C >= 0.0f;                           // false for padding rows and NaN feature rows
             const float init = live ? INFINITY : -INFINITY;        // -inf: nothing ever qualifies
             if (!live) C = 0.0f;
@@ -606,7 +607,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                 mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
-                if (p.debug == 1) {
+                if (p.skip_scan) {
                 } else if (nt == 0)
                     scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, Cpm, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt < p.nt_ref)
@@ -1512,7 +1513,7 @@ static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_
     if (blocks > 148 * 16) blocks = 148 * 16;
     tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, src_counts, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
                                                           crow, consts);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -1523,7 +1524,7 @@ static int launch_tc_list(const CUtensorMap &map_list, const TcParams &p, cudaSt
     auto kern = score_tc_kernel<KN, true>;
     PHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<sm_count(), NTHREADS, SMEM_BYTES, st>>>(map_list, p);       // persistent; the number of rows is read on the device
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -1535,7 +1536,7 @@ static int launch_tc(const CUtensorMap &map_a, const TcParams &p, cudaStream_t s
     if (grid > p.n_mtiles) grid = p.n_mtiles;
     const bool timed = g_tc_ring.begin(st);
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, p);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     if (timed) g_tc_ring.end(st);
     return PHM_OK;
 }
@@ -1605,7 +1606,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
     p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.consts = w.consts; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo; p.thr_out = w.thr_out;
     p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
-    p.debug = score_debug;
+    p.skip_scan = score_force_fallback;
     p.list_count = w.list_count; p.list_max_rows = w.list_max_rows; p.list_thr = w.list_thr; p.list_cnt = w.list_cnt;
     p.list_off = w.list_off; p.list_cols = nullptr;
     switch (a.k_neighbors) {
@@ -1633,13 +1634,13 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     int64_t blocks = (n + 255) / 256;                                  // a warp takes 32 consecutive rows at a time
     if (blocks > 148 * 16) blocks = 148 * 16;
     score_decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
 
     // rows whose candidate buffer overflowed but whose threshold is final: second tensor-core pass that lists every reference
     // under the threshold, then the exact decision over the lists (row count read on the device: no host synchronisation)
     if (use_list) {
         tc_list_gather_kernel<<<sm_count(), 256, 0, st>>>(w.a_op, w.crow, w.list_rows, w.list_count, w.list_max_rows, w.a_list, w.list_crow, w.list_cnt);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
         CUtensorMap map_list;
         if ((rc = make_map(&map_list, w.a_list, w.list_max_rows)) != PHM_OK) return rc;
         TcParams pl = p;
@@ -1655,7 +1656,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
             if (pass == 0) {
                 tc_list_scan_kernel<<<1, 1024, 0, st>>>(w.list_count, w.list_max_rows, (unsigned long long)w.list_pool_entries, w.list_cnt,
                                                         w.list_n, w.list_off);
-                PHM_CUDA_CHECK(cudaGetLastError());
+                PHM_LAUNCH_CHECK();
             }
         }
         ListDecideParams ld;
@@ -1669,7 +1670,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
         ld.fallback_rows = w.fallback_rows; ld.fallback_count = w.fallback_count;
         ld.rows_listed = w.rows_listed;
         score_list_decide_kernel<<<sm_count() * 2, 256, 0, st>>>(ld);
-        PHM_CUDA_CHECK(cudaGetLastError());
+        PHM_LAUNCH_CHECK();
     }
 
     // rows whose candidate buffer overflowed: exhaustive float64, count read on the device
@@ -1683,10 +1684,10 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     f.parts = w.fb_parts; f.tickets = w.fb_tickets;
     PHM_CUDA_CHECK(cudaMemsetAsync(w.fb_tickets, 0, sizeof(unsigned int) * FB_GRID, st));
     score_fallback_kernel<<<FB_GRID, 256, 0, st>>>(f);                 // few rows: column slices across CTAs
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     PHM_CUDA_CHECK(cudaFuncSetAttribute(score_fallback_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FBB_SMEM));
     score_fallback_blocked_kernel<<<sm_count(), 256, FBB_SMEM, st>>>(f);   // many rows: 32 per CTA share the reference stream
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 

@@ -76,7 +76,7 @@ extern "C" int phm_synth_lengths(uint64_t seed, int64_t first_contig, int64_t n_
     int64_t blocks = (n_contigs + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     synth_lengths_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, first_contig, n_contigs, d_lengths);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
 
@@ -88,6 +88,6 @@ extern "C" int phm_synth_bases(uint64_t seed, int64_t first_contig, int64_t n_co
     int64_t blocks = (n_contigs + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     synth_bases_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, first_contig, n_contigs, d_offsets, d_seq);
-    PHM_CUDA_CHECK(cudaGetLastError());
+    PHM_LAUNCH_CHECK();
     return PHM_OK;
 }

@@ -180,21 +180,21 @@ def get_kmer_index(kmer, symbols):
 
 
 def normalize_counts(counts):
-    """scripts/kmer.py:209.  float64 copy with every row divided by its sum (an all-zero row gives NaN, as there)."""
+    """scripts/kmer.py:209.  float64 copy with every row divided by its sum (an all-zero row gives NaN, as there).  Any numeric
+    array is taken, as by the reference: exact counts below 2^32 go through the integer kernel (bit-identical to numpy), anything
+    else -- summed genome counts of count_directory, already-float features, negative values -- through the float64 one."""
     import torch
     from . import ops, _lib
     _lib.require_cuda()
     arr = np.asarray(counts)
     if arr.size == 0:
         return arr.astype(float)
-    if arr.dtype.kind == "f":
-        if not (np.all(arr == np.floor(arr)) and arr.min() >= 0):
-            raise TypeError("normalize_counts on the device takes count data (non-negative integers)")
-    if arr.min() < 0 or arr.max() >= 2 ** 32:
-        raise TypeError("counts must fit an unsigned 32-bit integer")
-    as_u32 = np.ascontiguousarray(arr.astype(np.uint32))
-    dev = torch.from_numpy(as_u32.view(np.int32)).to("cuda")
-    return ops.normalize_cuda(dev).cpu().numpy()
+    is_count = arr.dtype.kind in "iub" or (arr.dtype.kind == "f" and bool(np.all(np.isfinite(arr))) and bool(np.all(arr == np.floor(arr))))
+    if is_count and arr.min() >= 0 and arr.max() < 2 ** 32:
+        as_u32 = np.ascontiguousarray(arr.astype(np.uint32))
+        return ops.normalize_cuda(torch.from_numpy(as_u32.view(np.int32)).to("cuda")).cpu().numpy()
+    as_f64 = np.ascontiguousarray(arr, dtype=np.float64)
+    return ops.normalize_rows_cuda(torch.from_numpy(as_f64).to("cuda")).cpu().numpy()
 
 
 def kmers(k, symbols=DNA):

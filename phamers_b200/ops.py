@@ -11,18 +11,18 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 _workspaces = {}
-_last_score_ws = ["score"]    # which workspace the last scoring call used (score_stats reads its header)
-kernel_launches = 0          # kernels of libphamers_b200.so launched through this module (bench.py reports it)
+_last_score_ws = [None]      # the workspace the last scoring call used (score_stats reads its header)
 
 
-def _launched(n):
-    global kernel_launches
-    kernel_launches += n
+def kernel_launches():
+    """Kernels libphamers_b200.so has launched in this process (counted inside the library, one per <<< >>>)."""
+    return int(_lib.load().phm_kernel_launches())
 
 
 def _workspace(kind, nbytes):
-    dev = torch.cuda.current_device()
-    key = (kind, dev)
+    """Scratch memory of one call.  A workspace holds live kernel state (work counters, candidate lists), so it is private to
+    (kind, device, STREAM): calls in flight on different streams never share one."""
+    key = (kind, torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device="cuda")
@@ -30,11 +30,24 @@ def _workspace(kind, nbytes):
     return buf
 
 
+def _check(t, name, dtype, width=None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype):
+        raise TypeError("%s must be a CUDA %s tensor" % (name, dtype))
+    if width is not None and (t.dim() != 2 or t.shape[1] != width):
+        raise ValueError("%s must be [rows, %d]" % (name, width))
+    return t.contiguous()
+
+
 def _as_u8_cuda(seq):
+    """The kernels read the sequence with 128-bit loads: 16-byte aligned start, storage readable up to the next multiple of 16."""
     if not (isinstance(seq, torch.Tensor) and seq.is_cuda and seq.dtype == torch.uint8 and seq.is_contiguous()):
         raise TypeError("sequence buffer must be a contiguous CUDA uint8 tensor")
     if seq.data_ptr() % 16:
         raise ValueError("sequence buffer must be 16-byte aligned")
+    readable = seq.untyped_storage().nbytes() - seq.storage_offset()
+    if readable < (seq.numel() + 15) // 16 * 16:
+        raise ValueError("sequence storage must be readable up to the next multiple of 16 bytes (allocate %d more bytes)"
+                         % ((seq.numel() + 15) // 16 * 16 - readable))
     return seq
 
 
@@ -71,7 +84,6 @@ def count_cuda(seq, offsets, k, canonical=False, counts=True, freq=False, naive=
     ws = _workspace("count", ws_bytes)
     check(lib.phm_kmer_count(ptr(seq), ptr(offsets), n, int(k), flags, ptr(out_counts), ptr(out_freq),
                              ptr(ws), ws.numel(), stream_ptr()))
-    _launched((1 if n else 0) + (1 if canonical else 0) + (1 if (naive and freq and n) else 0))
     return (out_counts if counts else None), out_freq
 
 
@@ -83,7 +95,6 @@ def pack_cuda(seq):
     codes = torch.empty(((n + 15) // 16,), dtype=torch.int32, device="cuda")
     valid = torch.empty(((n + 31) // 32,), dtype=torch.int32, device="cuda")
     check(lib.phm_pack_fasta(ptr(seq), n, ptr(codes), ptr(valid), stream_ptr()))
-    _launched(1 if n else 0)
     return codes, valid
 
 
@@ -97,7 +108,6 @@ def count_packed_cuda(codes, valid, offsets, k, canonical=False, counts=True, fr
     ws = _workspace("count", lib.phm_kmer_count_workspace_bytes(n, 0, int(k), flags))
     check(lib.phm_kmer_count_packed(ptr(codes), ptr(valid), ptr(offsets), n, int(k), flags, ptr(out_counts),
                                     ptr(out_freq), ptr(ws), ws.numel(), stream_ptr()))
-    _launched((1 if n else 0) + (1 if canonical else 0))
     return out_counts, out_freq
 
 
@@ -110,8 +120,28 @@ def normalize_cuda(counts):
     two_d = counts.reshape(-1, counts.shape[-1])
     out = torch.empty(two_d.shape, dtype=torch.float64, device="cuda")
     check(lib.phm_normalize_counts(ptr(two_d), two_d.shape[0], two_d.shape[1], ptr(out), stream_ptr()))
-    _launched(1 if two_d.shape[0] else 0)
     return out.reshape(counts.shape)
+
+
+def normalize_rows_cuda(rows):
+    """kmer.normalize_counts for rows that are not exact 32-bit counts: float64[n, bins] (or [bins]) -> row / row sum."""
+    lib = _lib.require_cuda()
+    rows = _check(rows, "rows", torch.float64)
+    two_d = rows.reshape(-1, rows.shape[-1])
+    out = torch.empty_like(two_d)
+    check(lib.phm_normalize_rows(ptr(two_d), two_d.shape[0], two_d.shape[1], ptr(out), stream_ptr()))
+    return out.reshape(rows.shape)
+
+
+def distances_cuda(point, rows):
+    """learning.distances: float64 Euclidean distance of point[dim] to every row of rows[n, dim]."""
+    lib = _lib.require_cuda()
+    point, rows = _check(point, "point", torch.float64), _check(rows, "rows", torch.float64)
+    if rows.dim() != 2 or point.numel() != rows.shape[1]:
+        raise ValueError("point must have as many elements as rows has columns")
+    out = torch.empty((rows.shape[0],), dtype=torch.float64, device="cuda")
+    check(lib.phm_distances(ptr(point), ptr(rows), rows.shape[0], rows.shape[1], ptr(out), stream_ptr()))
+    return out
 
 
 def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=None):
@@ -134,16 +164,11 @@ def score_cuda(points, refs, n_positive, cent_pos, cent_neg, k_neighbors=3, out=
     knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
     ws_bytes = lib.phm_score_workspace_bytes(n, refs.shape[0], cent_pos.shape[0], cent_neg.shape[0], dim)
     ws = _workspace("score", ws_bytes)
-    _last_score_ws[0] = "score"
+    _last_score_ws[0] = ws
     entry = lib.phm_score_counts if from_counts else lib.phm_score
     check(entry(ptr(points), n, dim, ptr(refs), refs.shape[0], int(n_positive),
                 ptr(cent_pos), cent_pos.shape[0], ptr(cent_neg), cent_neg.shape[0], int(k_neighbors),
                 ptr(knn), ptr(kmeans), ptr(combo), ptr(ws), ws.numel(), stream_ptr()))
-    if n:
-        # both paths: 4 row-preparation kernels (when non-empty) + scorer; the tensor-core path adds re-rank + exact fallback
-        tc_path = (dim == 256 and k_neighbors in (1, 3, 5) and refs.shape[0] >= k_neighbors and cent_pos.shape[0]
-                   and cent_neg.shape[0] and score_path_option != 1)
-        _launched(sum(1 for t in (points, refs, cent_pos, cent_neg) if t.shape[0]) + (8 if tc_path else 1))
     return knn, kmeans, combo
 
 
@@ -152,18 +177,19 @@ def count_score_cuda(seq, offsets, refs, n_positive, cent_pos, cent_neg, k_neigh
     Bit-identical to count_cuda followed by score_cuda on the counts; the histogram kernel prepares the scorer's operands."""
     lib = _lib.require_cuda()
     seq = _as_u8_cuda(seq)
+    if not (isinstance(offsets, torch.Tensor) and offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()):
+        raise TypeError("offsets must be a contiguous CUDA int64 tensor")
     n = offsets.numel() - 1
-    refs, cent_pos, cent_neg = (t.contiguous() for t in (refs, cent_pos, cent_neg))
+    refs, cent_pos, cent_neg = (_check(t, name, torch.float64, 256) for t, name in
+                                ((refs, "refs"), (cent_pos, "cent_pos"), (cent_neg, "cent_neg")))
     counts = _result(out_counts, (n, 256), torch.int32)
     knn, kmeans, combo = (_result(t, (n,), torch.float64) for t in (out if out is not None else (None, None, None)))
     ws_bytes = lib.phm_count_score_workspace_bytes(n, seq.numel(), refs.shape[0], cent_pos.shape[0], cent_neg.shape[0])
     ws = _workspace("count_score", ws_bytes)
-    _last_score_ws[0] = "count_score"
+    _last_score_ws[0] = ws
     check(lib.phm_count_score(ptr(seq), ptr(offsets), n, ptr(refs), refs.shape[0], int(n_positive), ptr(cent_pos), cent_pos.shape[0],
                               ptr(cent_neg), cent_neg.shape[0], int(k_neighbors), ptr(counts), ptr(knn), ptr(kmeans), ptr(combo),
                               ptr(ws), ws.numel(), stream_ptr()))
-    if n:
-        _launched(3 + 1 + 8)          # 3 reference preparations, histogram (+ operands), contraction, decision, list pass (5), fallback (2)
     return counts, knn, kmeans, combo
 
 
@@ -182,7 +208,7 @@ def score_stats():
     needed exact re-measurement, and (with _lib.set_option('score_stats', 1)) how much of the proven error interval the
     true ranking values use (must stay <= 1) and the largest ranking error in squared-distance units."""
     lib = _lib.require_cuda()
-    ws = _workspaces[(_last_score_ws[0], torch.cuda.current_device())]
+    ws = _last_score_ws[0]
     rows, err = ctypes.c_uint64(0), (ctypes.c_float * 4)()
     check(lib.phm_score_stats(ptr(ws), ctypes.byref(rows), err, stream_ptr()))
     return {"fallback_rows": int(rows.value), "max_bound_usage": float(err[0]), "max_rank_error": float(err[1]),
@@ -207,7 +233,6 @@ def fasta_scan_cuda(raw):
     header_pos = torch.empty((max(n_records, 1),), dtype=torch.int64, device="cuda")
     check(lib.phm_fasta_extract(ptr(raw), n, ptr(result), ptr(seq), ptr(offsets), ptr(header_pos), n_records, ptr(ws), ws_bytes,
                                 stream_ptr()))
-    _launched(3)
     return seq, offsets, header_pos[:n_records], bool(odd)
 
 

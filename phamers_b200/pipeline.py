@@ -35,6 +35,8 @@ class ContigScorer(object):
         self.cent_neg = torch.from_numpy(np.ascontiguousarray(centroids[1], dtype=np.float64)).cuda()
         self._staging = None
         self._host_out = None
+        self._copy_stream = None
+        self._chunk_counts = None
 
     # -- device resident --------------------------------------------------------------------------------
     def score_device(self, seq, offsets, method="combo", return_counts=True):
@@ -45,24 +47,56 @@ class ContigScorer(object):
         return counts, {"knn": knn, "kmeans": kmeans, "combo": combo}[method]
 
     # -- host buffers -----------------------------------------------------------------------------------
+    HOST_CHUNKS = 8                    # upload / compute pipeline depth of score_host
+
     def score_host(self, seq, offsets, method="combo"):
-        """seq: uint8 host tensor / ndarray with all contigs end to end, offsets: int64[n+1].  Host->device copy of
-        the bases and offsets, the three stages, and the device->host copy of the scores all happen here."""
+        """seq: uint8 host tensor / ndarray with all contigs end to end (pinned memory makes the copies asynchronous), offsets:
+        int64[n+1].  The contigs are cut into HOST_CHUNKS ranges of about equal bases; range i + 1 is copied to the device on a
+        copy stream while range i is counted and scored, and the scores come back in one copy at the end.  The host -> device
+        copy (16 GB per million contigs against ~9 ms of compute) is what bounds this call: see DESIGN.md section 7."""
         seq_t = seq if isinstance(seq, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(seq))
         off_t = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
-        total = seq_t.numel()
-        padded = (total + 15) // 16 * 16 + 16
+        n = off_t.numel() - 1
+        if n <= 0:
+            return np.zeros((0,), dtype=np.float64)
+        host_off = off_t.numpy()
+        total = int(host_off[-1] - host_off[0])
+        n_chunks = max(1, min(self.HOST_CHUNKS, n, total // (1 << 22) + 1))
+        targets = host_off[0] + (total * np.arange(1, n_chunks, dtype=np.float64) / n_chunks)
+        cuts = np.unique(np.concatenate(([0], np.clip(np.searchsorted(host_off, targets, side="left"), 0, n), [n])))
+        padded = (total + 15) // 16 * 16 + 32 * len(cuts)
         if self._staging is None or self._staging.numel() < padded:
             self._staging = torch.empty((padded,), dtype=torch.uint8, device="cuda")
-        d_seq = self._staging[:total]
-        d_seq.copy_(seq_t, non_blocking=True)
+        if self._host_out is None or self._host_out.numel() < n:
+            self._host_out = torch.empty((n,), dtype=torch.float64, pin_memory=True)             # pinned once, reused
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
         d_off = off_t.to("cuda", non_blocking=True)
-        _, scores = self.score_device(d_seq, d_off, method=method, return_counts=False)
-        if self._host_out is None or self._host_out.numel() < scores.numel():
-            self._host_out = torch.empty((scores.numel(),), dtype=torch.float64, pin_memory=True)   # pinned once, reused
-        out = self._host_out[:scores.numel()]
+        scores = torch.empty((n,), dtype=torch.float64, device="cuda")
+        widest = int(np.max(np.diff(cuts)))
+        if self._chunk_counts is None or self._chunk_counts.shape[0] < widest:
+            self._chunk_counts = torch.empty((widest, 256), dtype=torch.int32, device="cuda")
+        self._copy_stream.wait_stream(main)                                  # the staging buffer may still be read by an earlier call
+        uploads, place = [], 0
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            b0, b1 = int(host_off[lo]), int(host_off[hi])
+            dst = self._staging[place:place + (b1 - b0)]
+            with torch.cuda.stream(self._copy_stream):
+                dst.copy_(seq_t[b0:b1], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
+            uploads.append((int(lo), int(hi), b0, dst, done))
+            place += (b1 - b0 + 15) // 16 * 16 + 16                          # every range starts 16-byte aligned, padding readable
+        key = {"knn": 0, "kmeans": 1, "combo": 2}[method]
+        for lo, hi, b0, dst, done in uploads:
+            main.wait_event(done)
+            part = [torch.empty((hi - lo,), dtype=torch.float64, device="cuda") if i != key else scores[lo:hi] for i in range(3)]
+            ops.count_score_cuda(dst, d_off[lo:hi + 1] - b0, self.refs, self.n_positive, self.cent_pos, self.cent_neg, self.k_neighbors,
+                                 out_counts=self._chunk_counts[:hi - lo], out=tuple(part))
+        out = self._host_out[:n]
         out.copy_(scores, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
         return out.numpy().copy()
 
     def score_fasta(self, path, length_requirement=0, method="combo"):

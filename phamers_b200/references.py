@@ -81,7 +81,6 @@ def kmeans_assign_device(data, k):
     info = (ctypes.c_int64 * 3)()
     ops.check(lib.phm_kmeans_lloyd(ops.ptr(d_x), n, dim, ops.ptr(d_c), int(k), 300, tol, ops.ptr(d_labels), info, ops.ptr(ws), 256,
                                    ops.stream_ptr()))
-    ops._launched(2 * int(info[0]) + (0 if info[1] else 1))
     if info[2]:
         return kmeans_assign(data, k)
     return d_labels.cpu().numpy().astype(np.int32)

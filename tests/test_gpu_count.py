@@ -187,8 +187,8 @@ def test_properties_at_scale():
         # marginalising the last base of the k-mers gives the (k-1)-mers except the final window
         canon, _ = ops.count_cuda(seq, off, k, canonical=True)
         assert np.array_equal(_u32(canon).sum(axis=1), lengths - k + 1)
-    # a prefix against the oracle, byte for byte
-    n = 300
+    # a 10 000-contig prefix against the C oracle, byte for byte
+    n = 10000
     end = int(off[n].item())
     host_seq = seq[:end].cpu().numpy()
     host_off = off[:n + 1].cpu().numpy()
@@ -431,3 +431,23 @@ def test_count_directory_of_genome_files(tmp_path):
         assert list(ids) == list(want_ids) and len(ids) == 3
         assert counts.dtype == np.float64 and counts.shape == want.shape
         assert np.array_equal(counts, want)
+
+
+def test_normalize_counts_takes_any_numeric_rows():
+    """kmer.normalize_counts (reference scripts/kmer.py:209-221) is applied by the reference to whatever it is given: integer
+    counts, the float64 sums of count_directory (which can pass 2^32), features that are already normalised."""
+    from phamers_b200 import kmer
+    rng = np.random.default_rng(5)
+    ints = rng.integers(0, 5000, size=(40, 256))
+    assert np.array_equal(kmer.normalize_counts(ints), po.normalize_counts(ints))
+    sums = rng.integers(0, 2 ** 40, size=(7, 256)).astype(float)          # genome-directory sums: float, beyond 32 bits
+    assert np.array_equal(kmer.normalize_counts(sums), po.normalize_counts(sums))
+    feats = po.normalize_counts(ints) * 3.5                                # non-integer rows
+    got, want = kmer.normalize_counts(feats), po.normalize_counts(feats)
+    assert np.max(np.abs(got - want)) <= 1e-15 and got.dtype == np.float64
+    one_row = kmer.normalize_counts(sums[0])
+    assert one_row.shape == (256,) and np.array_equal(one_row, po.normalize_counts(sums[0]))
+    zero = np.zeros((2, 16))
+    assert np.isnan(kmer.normalize_counts(zero)).all()
+    neg = np.array([[1.0, -3.0, 4.0, 2.0]])
+    assert np.array_equal(kmer.normalize_counts(neg), po.normalize_counts(neg))

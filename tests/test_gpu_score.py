@@ -191,8 +191,10 @@ def test_full_path_properties_at_scale(scoring):
     for lo, hi in ((0, 270001), (270001, 270002), (270002, n)):
         o = (off[lo:hi + 1] - off[lo]).contiguous()
         s = seq[int(off[lo]):int(off[hi])]
-        if s.data_ptr() % 16:                                       # the C-ABI wants a 16-byte aligned sequence buffer
-            s = s.clone()
+        if s.data_ptr() % 16:                                       # the C-ABI wants a 16-byte aligned sequence buffer,
+            buf = torch.empty(((s.numel() + 15) // 16 * 16 + 16,), dtype=torch.uint8, device="cuda")   # readable to the next multiple of 16
+            buf[:s.numel()] = s
+            s = buf[:s.numel()]
         pieces.append(scorer.score_device(s, o)[1])
     assert torch.equal(torch.cat(pieces), combo)
 
@@ -207,8 +209,9 @@ def test_full_path_properties_at_scale(scoring):
     assert torch.equal(e_knn, knn[idx])
     assert float((e_combo - combo[idx]).abs().max()) <= 1e-12
 
-    # a prefix against the CPU oracle, end to end (bit-exact counts, scores within the stated tolerance)
-    m = 200
+    # the 10 000-contig prefix of SURVEY.md 8(d) config 2 against the CPU oracle, end to end (bit-exact counts from the C
+    # restatement, scores within the stated tolerance from the numpy / scikit-learn restatement)
+    m = 10000
     end = int(off[m].item())
     want_counts = c_oracle.count(seq[:end].cpu().numpy(), off[:m + 1].cpu().numpy(), 4)
     assert np.array_equal(counts[:m].cpu().numpy().view(np.uint32).astype(np.int64), want_counts)
@@ -220,7 +223,7 @@ def test_full_path_properties_at_scale(scoring):
 @pytest.mark.parametrize("n_rows", [300, 2500])
 def test_fallback_kernels_match_exact_path(scoring, n_rows):
     """Both exhaustive fallback kernels (column slices across CTAs for few rows, 32 rows per CTA sharing the reference stream
-    for many) against the exhaustive float64 scorer: the debug option makes the tensor-core epilogue keep no candidates, so
+    for many) against the exhaustive float64 scorer: option score_force_fallback makes the tensor-core epilogue keep no candidates, so
     every row goes down the fallback road."""
     import torch
     from phamers_b200 import _lib, ops, references
@@ -238,7 +241,7 @@ def test_fallback_kernels_match_exact_path(scoring, n_rows):
     cp = torch.from_numpy(np.ascontiguousarray(g["centroids_pos"])).cuda()
     cn = torch.from_numpy(np.ascontiguousarray(g["centroids_neg"])).cuda()
     try:
-        _lib.set_option("score_debug", 1)
+        _lib.set_option("score_force_fallback", 1)
         _lib.set_option("score_list_pass", 0)                            # otherwise the list pass would take these rows (see below)
         f_knn, f_km, f_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
         assert ops.score_stats()["fallback_rows"] == n_rows - 1          # the NaN row never asks for a fallback
@@ -251,7 +254,7 @@ def test_fallback_kernels_match_exact_path(scoring, n_rows):
         assert st["rows_listed"] + st["fallback_rows"] == n_rows - 1
         assert (st["fallback_rows"] == 0) == (n_rows == 300) and st["rows_listed"] >= 1000 * (n_rows > 300)
     finally:
-        _lib.set_option("score_debug", 0)
+        _lib.set_option("score_force_fallback", 0)
         _lib.set_option("score_list_pass", 1)
     t_knn, t_km, t_combo = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, len(pos), cp, cn, 3)]
     try:
@@ -413,3 +416,20 @@ def test_enlarged_reference_parity(scoring):
                            centroids=(g["centroids_pos"], g["centroids_neg"]))
     assert np.max(np.abs(t_combo[pick] - want)) <= TOL
     assert np.array_equal(np.sign(t_combo[pick]), np.sign(want))
+
+
+def test_learning_distances_and_closest_to(scoring):
+    """learning.distances / learning.closest_to (reference scripts/learning.py:47-66) on the device against the oracle's numpy
+    restatement: distances to every centroid, and the nearest centroid returned as the row itself."""
+    from phamers_b200 import kmer, learning
+    g, pos, neg = scoring
+    cents = np.ascontiguousarray(g["centroids_pos"])
+    pts = kmer.normalize_counts(g["query_counts"][:25])
+    for p in pts:
+        got = learning.distances(p, cents)
+        want = po.distances(p, cents)
+        assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-15
+        assert np.array_equal(learning.closest_to(p, cents), po.closest_to(p, cents))
+    two_d = learning.distances(pts[:1], cents)                            # a [1, dim] point is accepted as well (:53-55)
+    assert np.array_equal(two_d, learning.distances(pts[0], cents))
+    assert np.array_equal(learning.closest_to(cents[7], cents), cents[7])

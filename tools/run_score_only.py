@@ -11,9 +11,6 @@ from phamers_b200 import ops, pipeline  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-from phamers_b200 import _lib  # noqa: E402
-if len(sys.argv) > 3:
-    _lib.set_option("score_debug", int(sys.argv[3]))
 scorer = pipeline.ContigScorer()
 seq, off = ops.synth_contigs(20260101, 0, n)
 _, freq = ops.count_cuda(seq, off, 4, counts=False, freq=True)
