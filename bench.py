@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contigs", type=int, default=1000000, help="contigs per GPU")
+    ap.add_argument("--total-contigs", type=int, default=0,
+                    help="BASELINE configs[3]: this many contigs in total, cut into one shard per GPU balanced by BASES (strong scaling)")
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--workload", default="shipped", choices=["shipped", "enlarged", "count"])
     ap.add_argument("--refs", type=int, default=1000000, help="reference rows of --workload enlarged")
@@ -294,8 +296,20 @@ def run_b200(args, rank, local_rank, world):
     peaks = measured_peaks()
 
     # ---- workload (untimed) ----
-    n = args.contigs
-    seq, offsets = ops.synth_contigs(SEED, rank * n, n)
+    shard_sizes = None
+    if args.total_contigs:
+        # strong scaling (BASELINE configs[3]): the whole workload's offsets (lengths only), shards by the prefix sum of bases
+        import ctypes
+        lengths = torch.empty((args.total_contigs,), dtype=torch.int64, device="cuda")
+        _lib.check(_lib.load().phm_synth_lengths(ctypes.c_uint64(SEED), 0, args.total_contigs, _lib.ptr(lengths), _lib.stream_ptr()))
+        all_off = np.concatenate(([0], np.cumsum(lengths.cpu().numpy())))
+        bounds = parallel.balanced_partition(all_off, world)
+        shard_sizes = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+        first, n = int(bounds[rank]), shard_sizes[rank]
+        del lengths
+    else:
+        first, n = rank * args.contigs, args.contigs
+    seq, offsets = ops.synth_contigs(SEED, first, n)
     bases = int(offsets[-1].item())
     scoring = args.workload != "count"
     if scoring and args.k != 4:
@@ -339,7 +353,7 @@ def run_b200(args, rank, local_rank, world):
             combo = buf_scores[2]
         e1.record(stream)
         if world > 1 and scoring:
-            gathered = parallel.gather_scores(combo, [n] * world)
+            gathered = parallel.gather_scores(combo, shard_sizes or [n] * world)
         else:
             gathered = combo
         if timed:
@@ -390,7 +404,7 @@ def run_b200(args, rank, local_rank, world):
     lengths = offsets[1:] - offsets[:-1]
     assert args.no_check or bool((counts.sum(dim=1, dtype=torch.int64) == lengths - (args.k - 1)).all()), "count row sums are wrong"
     if scoring and not args.no_check:
-        assert bool(torch.isfinite(gathered).all()) and gathered.numel() == n * world
+        assert bool(torch.isfinite(gathered).all()) and gathered.numel() == (sum(shard_sizes) if shard_sizes else n * world)
 
     # ---- end to end through the public API with HOST buffers (copies inside the timed region) ----
     e2e = None
@@ -413,7 +427,8 @@ def run_b200(args, rank, local_rank, world):
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-            assert np.array_equal(host_scores, gathered[rank * n:(rank + 1) * n].cpu().numpy())
+            lo = sum(shard_sizes[:rank]) if shard_sizes else rank * n
+            assert np.array_equal(host_scores, gathered[lo:lo + n].cpu().numpy())
             e2e = {"value": all_bases * args.e2e_steps / dt, "unit": "bases/s",
                    "h2d_bytes_per_step": int(bases + 8 * (n + 1)), "d2h_bytes_per_step": int(8 * n),
                    "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
@@ -475,18 +490,20 @@ def run_b200(args, rank, local_rank, world):
     value = all_bases * args.steps / (elapsed_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if shard_sizes else "weak", "vs_baseline": None,
         "dtype": "u8 bases -> u32 counts -> f64 features (formed in-kernel) -> f64 scores", "data": "synthetic",
         "config": {"workload": ("synthetic metagenome %d contigs/GPU, 1-100 kb lognormal lengths, k=%d (BASELINE configs[%s]), "
-                                % (n, args.k, {"shipped": "1", "enlarged": "4", "count": "2"}[args.workload]))
+                                % (n, args.k, "3" if shard_sizes else {"shipped": "1", "enlarged": "4", "count": "2"}[args.workload]))
                                + ("scored against %d %s reference rows + %d centroids, method combo"
                                   % (n_refs, "shipped" if args.workload == "shipped" else "synthetic", n_cent) if scoring
                                   else "counting + normalising only%s" % (", canonical bins" if args.canonical else "")),
                    "contigs_per_gpu": n, "bases_per_gpu": bases, "seed": SEED,
+                   "shards": ("%d contigs in total, shards balanced by bases (parallel.balanced_partition): %s contigs" % (args.total_contigs, shard_sizes))
+                             if shard_sizes else None,
                    "l2_policy": "inputs (%.1f GB of bases per step) are far larger than the 126 MB L2" % (bases / 1e9),
                    "parallelism": "contigs sharded over %d GPU(s), references replicated, one NCCL all-gather of scores" % world,
                    "options": args.opt},
-        "contigs_per_sec": n * world * args.steps / (elapsed_ms * 1e-3),
+        "contigs_per_sec": (sum(shard_sizes) if shard_sizes else n * world) * args.steps / (elapsed_ms * 1e-3),
         "kernels": {"count_ms": c_ms, "score_ms": s_ms, "score_tc_kernel_ms": tc_ms, "count_roofline": count_roof,
                     "score_roofline": score_roof, "score_stats": score_stats, "configs": configs},
         "roofline": dominant, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
