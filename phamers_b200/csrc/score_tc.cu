@@ -199,10 +199,13 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // 
 // 32 accumulator columns of this thread's row (already in registers): lower bounds and their minimum against the row's
 // threshold; only if some lane of the warp has a hit are the hits looked at, one warp-uniform column at a time.
 // INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
-template <int K, int CAP, bool INSERT, bool LABELLED>
+struct NoIssue { __device__ __forceinline__ void operator()() const {} };
+// issue_next() is called as soon as the accumulators in `r` have been consumed (r is dead from then on): the caller uses it to
+// start the tensor-memory load of the NEXT chunk into the same registers, so one copy of this code serves every chunk of a tile
+template <int K, int CAP, bool INSERT, bool LABELLED, typename Issue = NoIssue>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
                                            int n_class, float C, float Cpm, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
-                                           uint32_t &flags, float (&drop_lo)[2]) {
+                                           uint32_t &flags, float (&drop_lo)[2], Issue issue_next = Issue()) {
     float lo[32], gm[8];
     // Quick reject with ONE constant per row instead of P_j per column: lo_j = RN(d_j - C P_j) >= RD(min_j d_j - RU(C pmax)) because
     // P_j <= pmax and rounding is monotone, so if that bound is already above the threshold in every lane the chunk has no hit and
@@ -216,6 +219,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs
         lo[4 * g + 3] = __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]);
         gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
     }
+    issue_next();
     const float limit0 = u[K - 1];
     {
         const float m0 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
@@ -311,6 +315,37 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
         bound_chunk<K>(rb, nbs_addr + 384u, p_addr + 384u, C, u);
         tmem_wait_ld();
     }
+    // The four chunks run through TWO copies of the scan code (a rolled loop over chunk pairs), not four.  With four inlined copies the
+    // kernel had 15 700 instructions and a fifth of the epilogue's issue slots was lost to instruction fetch (ncu: stall_no_inst 18 %);
+    // measured on 1 M contigs x 4510 references: 3.09 -> 2.84 ms.  A single copy (the next chunk loaded into the registers the scan has
+    // just consumed, PHM_SCAN_COPIES 1) shortens the window in which the tensor-memory load overlaps the scan and measures 2.87 ms.
+#ifndef PHM_SCAN_COPIES
+#define PHM_SCAN_COPIES 2
+#endif
+#if PHM_SCAN_COPIES == 1
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        auto next = [&]() { if (c < 3) tmem_ld32_issue(taddr + 32u * (uint32_t)(c + 1), ra); };
+        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 128u * (uint32_t)c, p_addr + 128u * (uint32_t)c, col0 + 32 * c, n_class, C, Cpm,
+                                                 cand_addr, first, u, cnt, flags, drop_lo, next);
+        __syncwarp();
+        if (c < 3) tmem_wait_ld();
+    }
+#elif PHM_SCAN_COPIES == 2
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        tmem_ld32_issue(taddr + 64u * (uint32_t)h + 32u, rb);
+        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u * (uint32_t)h, p_addr + 256u * (uint32_t)h, col0 + 64 * h, n_class, C, Cpm,
+                                                 cand_addr, first, u, cnt, flags, drop_lo);
+        __syncwarp();
+        tmem_wait_ld();
+        if (h == 0) tmem_ld32_issue(taddr + 64u, ra);
+        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 256u * (uint32_t)h + 128u, p_addr + 256u * (uint32_t)h + 128u, col0 + 64 * h + 32, n_class,
+                                                 C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
+        __syncwarp();
+        if (h == 0) tmem_wait_ld();
+    }
+#else
     tmem_ld32_issue(taddr + 32u, rb);
     scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
     __syncwarp();
@@ -324,6 +359,7 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
     __syncwarp();
     tmem_wait_ld();
     scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
+#endif
 }
 
 // ---------------- list mode: second pass over the rows whose candidate buffer overflowed ----------------
