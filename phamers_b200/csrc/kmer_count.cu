@@ -635,6 +635,7 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
                         if (lane == 0) {
                             emit.cnorm[c] = sc;
                             emit.crow[c] = tc::query_crow(sc, sd, sh, emit.consts->rho, emit.consts->pmax);
+                            emit.total[c] = (uint32_t)total;
                         }
                     }
                 } else {
@@ -712,6 +713,7 @@ __global__ void __launch_bounds__(256) hist_finish_kernel(const __grid_constant_
             if (lane == 0) {
                 emit.cnorm[c] = sc;
                 emit.crow[c] = tc::query_crow(sc, sd, sh, emit.consts->rho, emit.consts->pmax);
+                emit.total[c] = (uint32_t)total;
             }
         }
         if (job.freq) {

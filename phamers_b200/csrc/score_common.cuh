@@ -36,6 +36,7 @@ struct QueryEmit {             // where a producer of count rows writes the scor
     __half *op;                // [n, 256] centred, 2^12-scaled FP16 rows
     float *crow;               // [n] error constant C_row (NaN for an empty contig)
     double *cnorm;             // [n] |x - 1/256|^2
+    uint32_t *total;           // [n] row total of the counts (the decision kernel forms count / total without a reduction)
     const PrepConsts *consts;
 };
 constexpr int PREP_DIM = 256;

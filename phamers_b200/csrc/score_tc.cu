@@ -694,7 +694,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
 // This lane's 8 features of a query row: from the float64 feature matrix, or from raw counts divided by the row total
 // (IEEE float64 division, exactly what kmer.normalize_counts does, scripts/kmer.py:219-220).
 __device__ __forceinline__ void load_query_row(const double *points, const uint32_t *counts, int64_t row, int lane,
-                                               double (&x)[KDIM / 32]) {
+                                               double (&x)[KDIM / 32], uint32_t *total_out = nullptr) {
     if (counts) {
         uint32_t c[KDIM / 32];
         unsigned long long total = 0;
@@ -706,6 +706,7 @@ __device__ __forceinline__ void load_query_row(const double *points, const uint3
         const double r = 1.0 / t;                        // correctly rounded reciprocal, once per row
 #pragma unroll
         for (int i = 0; i < KDIM / 32; ++i) x[i] = exact_quotient((double)c[i], t, r);
+        if (total_out) *total_out = (uint32_t)total;
     } else {
 #pragma unroll
         for (int i = 0; i < KDIM / 32; ++i) x[i] = points[row * KDIM + lane + 32 * i];
@@ -726,7 +727,7 @@ __device__ __forceinline__ void load_query_row(const double *points, const uint3
 __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
                                     const uint32_t *__restrict__ src_counts, int is_ref, int64_t n_positive, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
                                     float *__restrict__ nbs, float *__restrict__ pnorm, float *__restrict__ crow,
-                                    PrepConsts *consts) {
+                                    PrepConsts *consts, uint32_t *__restrict__ row_total) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -737,7 +738,9 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
         double s = 0.0, sc = 0.0, sd = 0.0, sh = 0.0;       // |x|^2, |x - u|^2, |B~ - B|^2, |B|^2 (scaled units)
         const int64_t sr = (r < n_src) ? (perm_a * r + perm_c) % n_src : 0;
         double xs[KDIM / 32];
-        if (r < n_src) load_query_row(src, src_counts, sr, lane, xs);
+        uint32_t total = 0u;
+        if (r < n_src) load_query_row(src, src_counts, sr, lane, xs, &total);
+        if (row_total && src_counts && lane == 0 && r < n_src) row_total[sr] = total;
 #pragma unroll
         for (int i = 0; i < KDIM / 32; ++i) {
             const double x = (r < n_src) ? xs[i] : shift;
@@ -781,6 +784,7 @@ struct DecideParams {
     const double *cent_pos; int64_t n_cent_pos;
     const double *cent_neg; int64_t n_cent_neg;
     const double *cnorm_points;        // centred squared norms of the query rows (NaN = NaN feature row)
+    const uint32_t *row_total;         // row totals of the count rows (written by whoever prepared the query operands)
     const uint2 *cand; const float *cand_up; const uint32_t *meta; const float2 *drop_lo; const float *thr;
     int k_neighbors;
     double *knn, *kmeans, *combo;
@@ -810,113 +814,208 @@ __device__ __forceinline__ double warp_min_d(double v) {
     return v;
 }
 
-// One warp per contig; lane l < 16 holds candidate slot l (0..9 references, 10..12 positive centroids, 13..15 negative).
-// A warp takes 32 consecutive rows at a time: the cooperative part (gathers, reductions) row by row, then the scalar tail --
-// two square roots, a division and a float64 tanh, ~250 FP64 instructions that would otherwise be issued once per ROW with one
-// useful lane -- once per BATCH with lane = row, followed by coalesced stores.
-__global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
+// The decision of a row has a SCALAR part -- which of its (at most 16) candidates can still matter, and whether the neighbour vote
+// is already settled by the proven intervals -- and a part that needs the whole 256-wide row: the exact float64 distances to the one
+// or two centroids of each class that survive, and to the band of references when the intervals leave the vote open.  Round 1 ran
+// everything warp-wide, one row at a time (795 warp instructions per row, issue-bound).  Now a warp takes 32 consecutive rows and
+//   A  every LANE settles the scalar part of its own row from the candidate slots (no shuffles, no reductions),
+//   B  the WARP walks the rows that need exact distances (all live rows: the centroid term is always exact) with the row's
+//      features spread over the lanes; the row total comes from the producer of the counts (histogram kernel or preparation
+//      kernel), so the features are formed without a reduction,
+//   C  every lane finishes its row: two square roots, a division and a float64 tanh, then coalesced stores.
+constexpr uint32_t ROW_DECIDED = 0u, ROW_OPEN = 1u, ROW_FALLBACK = 2u;
+
+__device__ __forceinline__ int64_t cand_ref_index(const DecideParams &p, uint32_t col) {
+    return (int64_t)(((unsigned long long)p.perm_a * col + (unsigned long long)p.perm_c) % (unsigned long long)p.n_refs);
+}
+
+#ifndef PHM_DECIDE_MIN_CTAS
+#define PHM_DECIDE_MIN_CTAS 3
+#endif
+template <bool FROM_COUNTS>
+__global__ void __launch_bounds__(256, PHM_DECIDE_MIN_CTAS) score_decide_kernel(DecideParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int kn = p.k_neighbors;
     const bool has_cent = p.n_cent_pos > 0 && p.n_cent_neg > 0;
     for (int64_t base = warp * 32; base < p.n_points; base += n_warps * 32) {
-    const int n_here = (int)(p.n_points - base < 32 ? p.n_points - base : 32);
-    double my_knn = NAN, my_e0 = INFINITY, my_e1 = INFINITY;
-    float my_thr = 0.f;
-    bool my_fallback = false, my_listable = false, my_live = false;
-    for (int rr = 0; rr < n_here; ++rr) {
-        const int64_t row = base + rr;
-        const double na = p.cnorm_points[row];
-        bool fallback = false, listable = false;
-        float list_thr = 0.f;
-        double knn = NAN;
-        double row_e0 = INFINITY, row_e1 = INFINITY;
-        if (!isnan(na)) {
-            double x[KDIM / 32];
-            load_query_row(p.points, p.point_counts, row, lane, x);
-            const uint32_t meta = p.meta[row];
+        // ---------------- A: lane = row ----------------
+        const int64_t my_row = base + lane;
+        bool my_live = false;
+        uint32_t state = ROW_DECIDED, band = 0u, keep_p = 0u, keep_n = 0u;
+        uint32_t first_p = 0u, first_n = 0u;                        // centroid index of the lowest kept slot of each class
+        bool all_cent = false;
+        double my_knn = NAN;
+        float my_thr = 0.f;
+        if (my_row < p.n_points) my_live = !isnan(p.cnorm_points[my_row]);
+        if (my_live) {
+            const uint32_t meta = p.meta[my_row];
             const int cnt_r = meta & 255, cnt_p = (meta >> 8) & 255, cnt_n = (meta >> 16) & 255;
-            const float2 dropped = p.drop_lo[row];                      // smallest lower bound of a dropped negative / positive reference
-            const bool cent_overflow = (meta >> 24) != 0u;              // a centroid buffer overflowed: all centroids are measured below
-            // fewer kept candidates than k: the k smallest upper bounds belonged to candidates that were dropped when the buffer was
-            // full.  The kernel's own final threshold (over kept AND dropped candidates) is still valid, so the list pass can take the row.
-            fallback = cnt_r < kn;
-            listable = fallback;
-            list_thr = p.thr[row];
-            uint2 ent = make_uint2(0u, 0u);
-            float up_f = INFINITY;
-            if (lane < NENT) { ent = p.cand[row * NENT + lane]; up_f = p.cand_up[row * NENT + lane]; }
-            const bool is_ref = lane < CAP_R && lane < cnt_r;
-            const bool is_pos = lane >= CAP_R && lane < CAP_R + cnt_p && lane < CAP_R + CAP_C;
-            const bool is_neg = lane >= CAP_R + CAP_C && lane < CAP_R + CAP_C + cnt_n && lane < NENT;
-            const int col = (int)ent.y;
-            const bool valid = is_ref || is_pos || is_neg;
-            // the bounds are float values: every comparison below is exact in float (single shuffles, no float64 compares)
-            const float lower = valid ? __uint_as_float(ent.x) : INFINITY;
-            const float upper = valid ? up_f : INFINITY;
-            const double width = valid ? (double)upper - (double)lower : 0.0;
-            int my_idx = col;                                          // index in the caller's arrays
-            if (is_ref) my_idx = (int)((p.perm_a * (int64_t)col + p.perm_c) % p.n_refs);
-
-            // ---------------- k nearest references ----------------
-            if (!fallback) {
-                int rank = 0;                                          // position of my upper bound among the candidates'
+            const uint4 *cq = reinterpret_cast<const uint4 *>(p.cand + my_row * NENT);          // two (lower bits, column) entries per load
+            const float4 *uq = reinterpret_cast<const float4 *>(p.cand_up + my_row * NENT);
+            my_thr = p.thr[my_row];
+            // ---- k nearest references: slots 0 .. cnt_r - 1 ----
+            if (cnt_r < kn) {
+                // fewer kept candidates than k: the k smallest upper bounds belonged to candidates that were dropped when the buffer
+                // was full.  The kernel's own final threshold (over kept AND dropped candidates) is still valid: list pass.
+                state = ROW_FALLBACK;
+            } else {
+                float lower[CAP_R], upper[CAP_R];
+                uint32_t col[CAP_R];
+#pragma unroll
+                for (int h = 0; h < CAP_R / 2; ++h) {
+                    const uint4 e = cq[h];
+                    lower[2 * h] = __uint_as_float(e.x); col[2 * h] = e.y;
+                    lower[2 * h + 1] = __uint_as_float(e.z); col[2 * h + 1] = e.w;
+                }
+                {
+                    const float4 u0 = uq[0], u1 = uq[1];
+                    const float2 u2 = *reinterpret_cast<const float2 *>(p.cand_up + my_row * NENT + 8);
+                    upper[0] = u0.x; upper[1] = u0.y; upper[2] = u0.z; upper[3] = u0.w;
+                    upper[4] = u1.x; upper[5] = u1.y; upper[6] = u1.z; upper[7] = u1.w;
+                    upper[8] = u2.x; upper[9] = u2.y;
+                }
+                // the k-th smallest upper bound (ties: lower slot first); the bounds are floats, every comparison is exact
+                float u_k = INFINITY;
 #pragma unroll
                 for (int s = 0; s < CAP_R; ++s) {
-                    const float ou = __shfl_sync(FULL, upper, s);
-                    if (s < cnt_r && s != lane && (ou < upper || (ou == upper && s < lane))) ++rank;
+                    int rank = 0;
+#pragma unroll
+                    for (int t = 0; t < CAP_R; ++t)
+                        rank += (t != s && t < cnt_r && (upper[t] < upper[s] || (upper[t] == upper[s] && t < s))) ? 1 : 0;
+                    if (s < cnt_r && rank == kn - 1) u_k = upper[s];
                 }
-                const unsigned kth = __ballot_sync(FULL, is_ref && rank == kn - 1);
-                const float u_k = __shfl_sync(FULL, upper, __ffs(kth) - 1);
-                const bool in_band = is_ref && lower <= u_k;
-                const unsigned band = __ballot_sync(FULL, in_band);
-                const unsigned pos_mask = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
+                uint32_t pos_mask = 0u;
+#pragma unroll
+                for (int s = 0; s < CAP_R; ++s) {
+                    if (s < cnt_r && lower[s] <= u_k) {
+                        band |= 1u << s;
+                        if (cand_ref_index(p, col[s]) < p.n_positive) pos_mask |= 1u << s;
+                    }
+                }
                 const int n_band = __popc(band);
+                const float2 dropped = p.drop_lo[my_row];                 // smallest lower bound of a dropped negative / positive reference
                 const bool lost_neg = dropped.x <= u_k, lost_pos = dropped.y <= u_k;
                 if (lost_neg || lost_pos) {
                     // a dropped candidate could still be among the k nearest: only a unanimous vote over kept AND dropped ones
                     // can be read off
-                    if (pos_mask == band && !lost_neg) knn = 1.0;
-                    else if (pos_mask == 0u && !lost_pos) knn = -1.0;
-                    else { fallback = true; listable = true; }
+                    if (pos_mask == band && !lost_neg) my_knn = 1.0;
+                    else if (pos_mask == 0u && !lost_pos) my_knn = -1.0;
+                    else state = ROW_FALLBACK;
                 } else if (n_band == kn || pos_mask == 0u || pos_mask == band) {
                     // the k nearest are exactly the band, or every possible member votes the same way
                     const int pos = (pos_mask == band) ? kn : ((pos_mask == 0u) ? 0 : __popc(pos_mask));
-                    knn = (2 * pos > kn) ? 1.0 : -1.0;               // 2 * (predict - 0.5), scripts/learning.py:128
+                    my_knn = (2 * pos > kn) ? 1.0 : -1.0;               // 2 * (predict - 0.5), scripts/learning.py:128
                 } else {
-                    // undecided: exact distances of the band, k smallest (ties: lower reference index first)
-                    double my_d2 = INFINITY;
-                    unsigned rest = band;
-                    while (rest) {
-                        const int s = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        const int idx = __shfl_sync(FULL, my_idx, s);
-                        const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
-                        if (lane == s) my_d2 = d;
-                    }
-                    int erank = 0;
-                    rest = band;
-                    while (rest) {
-                        const int s = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        const double od = __shfl_sync(FULL, my_d2, s);
-                        const int oi = __shfl_sync(FULL, my_idx, s);
-                        if (s != lane && (od < my_d2 || (od == my_d2 && oi < my_idx))) ++erank;
-                    }
-                    const unsigned top = __ballot_sync(FULL, in_band && erank < kn);
-                    const int pos = __popc(top & pos_mask);
-                    knn = (2 * pos > kn) ? 1.0 : -1.0;
-                    if (p.rows_remeasured && lane == 0) atomicAdd(p.rows_remeasured, 1ull);
+                    state = ROW_OPEN;                                    // exact distances of the band decide (part B)
                 }
             }
+            // ---- nearest centroid of each class: slots CAP_R .. (positive), CAP_R + CAP_C .. (negative) ----
+            if (has_cent) {
+                all_cent = (meta >> 24) != 0u || cnt_p < 1 || cnt_n < 1;  // more than CAP_C centroids inside the nearest one's interval
+                if (!all_cent) {
+                    float lo_c[2 * CAP_C], up_c[2 * CAP_C];
+                    const uint4 e0 = cq[CAP_R / 2], e1 = cq[CAP_R / 2 + 1], e2 = cq[CAP_R / 2 + 2];
+                    {
+                        lo_c[0] = __uint_as_float(e0.x); lo_c[1] = __uint_as_float(e0.z); lo_c[2] = __uint_as_float(e1.x);
+                        lo_c[3] = __uint_as_float(e1.z); lo_c[4] = __uint_as_float(e2.x); lo_c[5] = __uint_as_float(e2.z);
+                        const float2 a = *reinterpret_cast<const float2 *>(p.cand_up + my_row * NENT + 10);
+                        const float4 b = uq[3];
+                        up_c[0] = a.x; up_c[1] = a.y; up_c[2] = b.x; up_c[3] = b.y; up_c[4] = b.z; up_c[5] = b.w;
+                    }
+                    float u_p = INFINITY, u_n = INFINITY;
+#pragma unroll
+                    for (int s = 0; s < CAP_C; ++s) {
+                        if (s < cnt_p) u_p = fminf(u_p, up_c[s]);
+                        if (s < cnt_n) u_n = fminf(u_n, up_c[CAP_C + s]);
+                    }
+                    const uint32_t col_c[2 * CAP_C] = {e0.y, e0.w, e1.y, e1.w, e2.y, e2.w};
+#pragma unroll
+                    for (int s = CAP_C - 1; s >= 0; --s) {                 // descending: first_* end up with the LOWEST kept slot
+                        if (s < cnt_p && lo_c[s] <= u_p) { keep_p |= 1u << s; first_p = col_c[s]; }
+                        if (s < cnt_n && lo_c[CAP_C + s] <= u_n) { keep_n |= 1u << s; first_n = col_c[CAP_C + s]; }
+                    }
+                }
+            }
+        }
+        const uint32_t my_info = state | (band << 2) | (keep_p << 12) | (keep_n << 15) | ((all_cent ? 1u : 0u) << 18);
+
+        // ---------------- B: warp = row, for every live row of the batch ----------------
+        double my_e0 = INFINITY, my_e1 = INFINITY;
+        unsigned todo = __ballot_sync(FULL, my_live && (has_cent || state == ROW_OPEN || p.stats != nullptr));
+        // the count row (or feature row) of the NEXT row to do is fetched while the current one is worked on: the loop is a chain of
+        // dependent memory accesses per row otherwise
+        uint32_t c_nxt[FROM_COUNTS ? KDIM / 32 : 1], t_nxt = 0u;
+        double x_nxt[FROM_COUNTS ? 1 : KDIM / 32];
+        auto fetch = [&](int rr) {
+            const int64_t row = base + rr;
+            if (FROM_COUNTS) {
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) c_nxt[FROM_COUNTS ? i : 0] = p.point_counts[row * KDIM + lane + 32 * i];
+                t_nxt = p.row_total[row];
+            } else {
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) x_nxt[FROM_COUNTS ? 0 : i] = p.points[row * KDIM + lane + 32 * i];
+            }
+        };
+        if (todo) fetch(__ffs(todo) - 1);
+        while (todo) {
+            const int rr = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t row = base + rr;
+            const uint32_t info = __shfl_sync(FULL, my_info, rr);
+            const uint32_t cp0 = __shfl_sync(FULL, first_p, rr), cn0 = __shfl_sync(FULL, first_n, rr);
+            double x[KDIM / 32];
+            if (FROM_COUNTS) {
+                const double t = (double)t_nxt;
+                const double r = 1.0 / t;                                 // correctly rounded reciprocal, once per row
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) x[i] = exact_quotient((double)c_nxt[FROM_COUNTS ? i : 0], t, r);
+            } else {
+#pragma unroll
+                for (int i = 0; i < KDIM / 32; ++i) x[i] = x_nxt[FROM_COUNTS ? 0 : i];
+            }
+            if (todo) fetch(__ffs(todo) - 1);
+            const uint2 *ent = p.cand + row * NENT;                       // warp-uniform reads below: one broadcast each
+            if ((info & 3u) == ROW_OPEN) {
+                // undecided: exact distances of the band, k smallest (ties: lower reference index first)
+                const uint32_t bnd = (info >> 2) & 1023u;
+                double my_d2 = INFINITY;
+                int64_t my_idx = 0;
+                unsigned rest = bnd;
+                while (rest) {
+                    const int s = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const int64_t idx = cand_ref_index(p, ent[s].y);
+                    const double d = warp_exact_d2(x, p.refs + idx * KDIM, lane);
+                    if (lane == s) { my_d2 = d; my_idx = idx; }
+                }
+                int erank = 0;
+                rest = bnd;
+                while (rest) {
+                    const int s = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const double od = __shfl_sync(FULL, my_d2, s);
+                    const int64_t oi = __shfl_sync(FULL, my_idx, s);
+                    if (s != lane && (od < my_d2 || (od == my_d2 && oi < my_idx))) ++erank;
+                }
+                const bool in_band = lane < CAP_R && ((bnd >> lane) & 1u);
+                const unsigned top = __ballot_sync(FULL, in_band && erank < kn);
+                const unsigned posm = __ballot_sync(FULL, in_band && my_idx < p.n_positive);
+                const double knn = (2 * __popc(top & posm) > kn) ? 1.0 : -1.0;
+                if (lane == rr) my_knn = knn;
+                if (p.rows_remeasured && lane == 0) atomicAdd(p.rows_remeasured, 1ull);
+            }
             if (p.stats) {                    // diagnostics: how much of the proven interval the true value uses
+                const uint32_t meta = p.meta[row];
+                const int cnt_r = meta & 255;
+                const double na = p.cnorm_points[row];
                 float worst_use = 0.f, worst_abs = 0.f;
-                for (int s = 0; s < CAP_R; ++s) {
-                    if (s >= cnt_r) break;
-                    const int idx = __shfl_sync(FULL, my_idx, s);
-                    const double lo_s = (double)__shfl_sync(FULL, lower, s), w_s = __shfl_sync(FULL, width, s);
-                    const double d = warp_exact_d2(x, p.refs + (int64_t)idx * KDIM, lane);
+                for (int s = 0; s < CAP_R && s < cnt_r; ++s) {
+                    const uint2 e = ent[s];
+                    const double lo_s = (double)__uint_as_float(e.x), w_s = (double)p.cand_up[row * NENT + s] - lo_s;
+                    const double d = warp_exact_d2(x, p.refs + cand_ref_index(p, e.y) * KDIM, lane);
                     const double exact = (d - na) * NORM_SCALE;                 // what the ranking value estimates
                     const double err = fabs(lo_s + 0.5 * w_s - exact);
                     worst_abs = fmaxf(worst_abs, (float)(err / NORM_SCALE));
@@ -927,19 +1026,11 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
                     atomicMax(reinterpret_cast<int *>(p.stats + 1), __float_as_int(worst_abs));
                 }
             }
-            // ---------------- nearest centroid of each class ----------------
             if (has_cent) {
                 double e2[2] = {INFINITY, INFINITY};
-                float u_p = is_pos ? upper : INFINITY, u_n = is_neg ? upper : INFINITY;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    u_p = fminf(u_p, __shfl_xor_sync(FULL, u_p, o));
-                    u_n = fminf(u_n, __shfl_xor_sync(FULL, u_n, o));
-                }
-                unsigned rest_p = __ballot_sync(FULL, is_pos && lower <= u_p);
-                unsigned rest_n = __ballot_sync(FULL, is_neg && lower <= u_n);
-                if (cent_overflow || cnt_p < 1 || cnt_n < 1) {
-                    // more than CAP_C centroids of a class inside the interval of the nearest one (rare): every centroid, exactly
+                unsigned rest_p = (info >> 12) & 7u, rest_n = (info >> 15) & 7u;
+                if ((info >> 18) & 1u) {
+                    // every centroid, exactly (rare)
                     rest_p = 0u; rest_n = 0u;
                     for (int64_t c = 0; c < p.n_cent_pos; c += 2) {
                         const int64_t c1 = c + 1 < p.n_cent_pos ? c + 1 : c;
@@ -952,11 +1043,13 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
                         e2[1] = fmin(e2[1], fmin(a0, a1));
                     }
                 }
+                bool first_round = true;                                 // the lowest kept slot of each class came along from part A
                 while (rest_p | rest_n) {                              // one candidate of each class per round: both rows in flight
                     const int sp = rest_p ? __ffs(rest_p) - 1 : 0, sn = rest_n ? __ffs(rest_n) - 1 : 0;
-                    const int ip = __shfl_sync(FULL, my_idx, sp), in_ = __shfl_sync(FULL, my_idx, sn);
-                    const double *bp = p.cent_pos + (int64_t)(rest_p ? ip : 0) * KDIM;
-                    const double *bn = p.cent_neg + (int64_t)(rest_n ? in_ : 0) * KDIM;
+                    const uint32_t ip = first_round ? cp0 : ent[CAP_R + sp].y, in_ = first_round ? cn0 : ent[CAP_R + CAP_C + sn].y;
+                    first_round = false;
+                    const double *bp = p.cent_pos + (int64_t)(rest_p ? ip : 0u) * KDIM;
+                    const double *bn = p.cent_neg + (int64_t)(rest_n ? in_ : 0u) * KDIM;
                     double ap = 0.0, an = 0.0;
 #pragma unroll
                     for (int i = 0; i < KDIM / 32; ++i) {
@@ -971,41 +1064,36 @@ __global__ void __launch_bounds__(256, 4) score_decide_kernel(DecideParams p) {
                     rest_p &= rest_p - 1;
                     rest_n &= rest_n - 1;
                 }
-                row_e0 = e2[0]; row_e1 = e2[1];
+                if (lane == rr) { my_e0 = e2[0]; my_e1 = e2[1]; }
             }
         }
-        if (lane == rr) {                                               // everything above is warp-uniform
-            my_knn = knn; my_e0 = row_e0; my_e1 = row_e1; my_thr = list_thr;
-            my_fallback = fallback; my_listable = listable; my_live = !isnan(na);
-        }
-    }
-    // ---------------- scalar tail: lane = row ----------------
-    if (lane < n_here) {
-        const int64_t row = base + lane;
-        double km = NAN;
-        if (my_live && has_cent) {
-            const double e_pos = sqrt(my_e0), e_neg = sqrt(my_e1);
-            km = tanh((e_neg - e_pos) / (e_pos + e_neg));              // scripts/phamer.py:206-209
-        }
-        if (my_fallback) {
-            bool listed = false;
-            if (my_listable && p.list_rows) {
-                const unsigned long long slot = atomicAdd(p.list_count, 1ull);
-                if (slot < (unsigned long long)p.list_max_rows) {
-                    p.list_rows[slot] = row; p.list_thr[slot] = my_thr; p.list_km[slot] = km;
-                    listed = true;
+
+        // ---------------- C: lane = row ----------------
+        if (my_row < p.n_points) {
+            double km = NAN;
+            if (my_live && has_cent) {
+                const double e_pos = sqrt(my_e0), e_neg = sqrt(my_e1);
+                km = tanh((e_neg - e_pos) / (e_pos + e_neg));              // scripts/phamer.py:206-209
+            }
+            if (my_live && state == ROW_FALLBACK) {
+                bool listed = false;
+                if (p.list_rows) {
+                    const unsigned long long slot = atomicAdd(p.list_count, 1ull);
+                    if (slot < (unsigned long long)p.list_max_rows) {
+                        p.list_rows[slot] = my_row; p.list_thr[slot] = my_thr; p.list_km[slot] = km;
+                        listed = true;
+                    }
                 }
+                if (!listed) {
+                    const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
+                    p.fallback_rows[slot_out] = my_row;
+                }
+            } else {
+                if (p.knn) p.knn[my_row] = my_knn;
+                if (p.kmeans) p.kmeans[my_row] = km;
+                if (p.combo) p.combo[my_row] = my_knn + km;                 // scripts/phamer.py:313
             }
-            if (!listed) {
-                const unsigned long long slot_out = atomicAdd(p.fallback_count, 1ull);
-                p.fallback_rows[slot_out] = row;
-            }
-        } else {
-            if (p.knn) p.knn[row] = my_knn;
-            if (p.kmeans) p.kmeans[row] = km;
-            if (p.combo) p.combo[row] = my_knn + km;                    // scripts/phamer.py:313
         }
-    }
     }
 }
 
@@ -1481,6 +1569,7 @@ struct TcWorkspace {
     uint2 *cand; float *cand_up; uint32_t *meta; float2 *drop_lo; float *thr_out;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
     double *cnorm_points;
+    uint32_t *row_total;
     int64_t *fallback_rows;
     FallbackPart *fb_parts; unsigned int *fb_tickets;
     size_t bytes;
@@ -1513,6 +1602,7 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.norm_cpos = reinterpret_cast<double *>(take((size_t)n_cp * 8));
     w.norm_cneg = reinterpret_cast<double *>(take((size_t)n_cn * 8));
     w.cnorm_points = reinterpret_cast<double *>(take((size_t)n * 8));
+    w.row_total = reinterpret_cast<uint32_t *>(take((size_t)n * 4));
     w.fallback_rows = reinterpret_cast<int64_t *>(take((size_t)n * 8));
     w.fb_parts = reinterpret_cast<FallbackPart *>(take(sizeof(FallbackPart) * FB_GRID * FB_SLICES));
     w.fb_tickets = reinterpret_cast<unsigned int *>(take(sizeof(unsigned int) * FB_GRID));
@@ -1543,12 +1633,13 @@ bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cp, 
 }
 
 static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, int64_t n_positive, __half *op,
-                       double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st) {
+                       double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st,
+                       uint32_t *row_total = nullptr) {
     if (n_rows == 0) return PHM_OK;
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, src_counts, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
-                                                          crow, consts);
+                                                          crow, consts, row_total);
     PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
@@ -1608,7 +1699,7 @@ int score_tc_begin(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t s
                           w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
     if ((rc = launch_prep(a.cent_neg, nullptr, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
                           w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
-    if (emit) { emit->op = w.a_op; emit->crow = w.crow; emit->cnorm = w.cnorm_points; emit->consts = w.consts; }
+    if (emit) { emit->op = w.a_op; emit->crow = w.crow; emit->cnorm = w.cnorm_points; emit->total = w.row_total; emit->consts = w.consts; }
     return PHM_OK;
 }
 
@@ -1630,7 +1721,8 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     int64_t perm_a, perm_c;
     ref_permutation(a.n_refs, &perm_a, &perm_c);
     if (!queries_prepared &&
-        (rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st)) != PHM_OK) return rc;
+        (rc = launch_prep(a.points, a.point_counts, n, n, 1, 0, 0, 0, w.a_op, w.norm_points, w.cnorm_points, nullptr, nullptr, w.crow, w.consts, st,
+                          w.row_total)) != PHM_OK) return rc;
 
     CUtensorMap map_a;
     if ((rc = make_map(&map_a, w.a_op, n)) != PHM_OK) return rc;
@@ -1658,7 +1750,7 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     r.refs = a.refs; r.n_refs = a.n_refs; r.n_positive = a.n_positive;
     r.perm_a = perm_a; r.perm_c = perm_c;
     r.cent_pos = a.cent_pos; r.n_cent_pos = a.n_cent_pos; r.cent_neg = a.cent_neg; r.n_cent_neg = a.n_cent_neg;
-    r.cnorm_points = w.cnorm_points; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta; r.drop_lo = w.drop_lo; r.thr = w.thr_out;
+    r.cnorm_points = w.cnorm_points; r.row_total = w.row_total; r.cand = w.cand; r.cand_up = w.cand_up; r.meta = w.meta; r.drop_lo = w.drop_lo; r.thr = w.thr_out;
     r.k_neighbors = a.k_neighbors;
     r.knn = a.knn; r.kmeans = a.kmeans; r.combo = a.combo;
     r.fallback_rows = w.fallback_rows; r.fallback_count = w.fallback_count;
@@ -1669,7 +1761,8 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     r.list_thr = w.list_thr; r.list_km = w.list_km;
     int64_t blocks = (n + 255) / 256;                                  // a warp takes 32 consecutive rows at a time
     if (blocks > 148 * 16) blocks = 148 * 16;
-    score_decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(r);
+    if (a.point_counts) score_decide_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(r);
+    else score_decide_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(r);
     PHM_LAUNCH_CHECK();
 
     // rows whose candidate buffer overflowed but whose threshold is final: second tensor-core pass that lists every reference
