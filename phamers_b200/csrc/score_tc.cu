@@ -78,6 +78,22 @@ constexpr double NORM_SCALE = 8388608.0;  // 2^23: ranking value = 2^23 (|b'|^2 
 constexpr float PAD_NORM = 3.0e38f;
 constexpr double EPS_ACC = 1.0 / 65536.0; // FP32 accumulation allowance relative to |A| |B|
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // F16 x F16 -> F32, K-major
+// Seventeenth k-step (round 2): 16 extra K columns turn the accumulator into the LOWER BOUND itself.  A row carries
+// (2^10, 2^-1, 2^-12, C16, 0 ...), a reference (-n1, -n2, -n3, P16, 0 ...), where n1 2^10 + n2 2^-1 + n3 2^-12 is the three-way FP16
+// split of nbs_j = 2^23 |b'_j|^2 (33 mantissa bits: exact for every float), C16 >= C_row and P16 >= P_j are rounded UP to FP16.  The
+// accumulator then holds  S_ij = 2^24 a'_i.b'_j - nbs_j + C16_i P16_j,  and  lo_ij = -S_ij <= x_ij - C_i P_j  is a valid lower bound
+// (a little more conservative: both factors were rounded up), up_ij = lo_ij + 2 C16_i P16_j a valid upper bound.  The epilogue is
+// a bare maximum over the accumulators: no per-column loads, no subtraction, no multiply-add, no quick reject.
+// The extra operands are 128 rows x 32 bytes in the NO-SWIZZLE K-major canonical layout (8 x 16-byte core matrices: row r, K half h
+// at (r >> 3) * 256 + h * 128 + (r & 7) * 16), prepared in that order in global memory and brought in by plain bulk copies: the
+// block of a reference tile and the two blocks of the contig tile travel together in a fifth slot of the B ring per tile.
+constexpr int XK = 16;
+constexpr int XBLK_BYTES = BM * XK * 2;   // 4 KB
+constexpr int XBLK_HALVES = XBLK_BYTES / 2;
+static_assert(3 * XBLK_BYTES <= BLOCK_BYTES, "the extra operands of a tile fit one ring slot");
+__host__ __device__ __forceinline__ int64_t xrow_offset(int64_t row) {      // in halves, K half 0 (K half 1, all zero, is 64 halves further)
+    return (row >> 7) * XBLK_HALVES + ((row & 127) >> 3) * 128 + (row & 7) * 8;
+}
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
 
 // ---------------- PTX helpers ----------------
@@ -110,6 +126,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
+}
+__device__ __forceinline__ float c16_up(float c) { return __half2float(__float2half_ru(c)); }
+// K-major, no swizzle: core matrices of 8 rows x 16 bytes; K halves 128 bytes apart (leading offset), 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_plain(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;           // leading byte offset: next core matrix along K
+    d |= (uint64_t)(256 >> 4) << 32;           // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    return d;                                  // layout type 0: no swizzle
 }
 // 32 consecutive accumulator columns of this thread's row; the result registers are valid after tmem_wait_ld()
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -200,42 +226,29 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {       // 
 // threshold; only if some lane of the warp has a hit are the hits looked at, one warp-uniform column at a time.
 // INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
 struct NoIssue { __device__ __forceinline__ void operator()() const {} };
-// issue_next() is called as soon as the accumulators in `r` have been consumed (r is dead from then on): the caller uses it to
-// start the tensor-memory load of the NEXT chunk into the same registers, so one copy of this code serves every chunk of a tile
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+    float g[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        g[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+    return fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+}
+// 32 accumulator columns of this thread's row (already in registers).  The accumulator IS the negated lower bound (see XK above):
+// the chunk's smallest lower bound is minus the largest accumulator, and only if it beats the row's threshold in some lane of the
+// warp are the hits looked at, one warp-uniform column at a time.
+// INSERT = false: the threshold is already final for these columns (second pass of a two-pass tile), hits are only collected.
+// issue_next() is called as soon as the accumulators in `r` are no longer needed by the common path.
 template <int K, int CAP, bool INSERT, bool LABELLED, typename Issue = NoIssue>
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c,
-                                           int n_class, float C, float Cpm, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t p_c, int col_c,
+                                           int n_class, float C, uint32_t cand_addr, int first, float (&u)[K], int &cnt,
                                            uint32_t &flags, float (&drop_lo)[2], Issue issue_next = Issue()) {
-    float lo[32], gm[8];
-    // Quick reject with ONE constant per row instead of P_j per column: lo_j = RN(d_j - C P_j) >= RD(min_j d_j - RU(C pmax)) because
-    // P_j <= pmax and rounding is monotone, so if that bound is already above the threshold in every lane the chunk has no hit and
-    // neither the P_j loads nor the 32 multiply-adds are needed (Cpm = RU(C * pmax), pmax = the largest P of the reference set).
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const uint4 nb = lds_v4(nbs_c + 16u * g);
-        lo[4 * g + 0] = __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]);
-        lo[4 * g + 1] = __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]);
-        lo[4 * g + 2] = __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]);
-        lo[4 * g + 3] = __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]);
-        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
-    }
-    issue_next();
     const float limit0 = u[K - 1];
-    {
-        const float m0 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-        if (!__any_sync(FULL, __fsub_rd(m0, Cpm) <= limit0)) return;
-    }
+    const float m = -max32(r);
+    if (!__any_sync(FULL, m <= limit0)) { issue_next(); return; }
+    float lo[32];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const uint4 pp = lds_v4(p_c + 16u * g);
-        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), lo[4 * g + 0]);
-        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), lo[4 * g + 1]);
-        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), lo[4 * g + 2]);
-        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), lo[4 * g + 3]);
-        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
-    }
-    const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-    if (!__any_sync(FULL, m <= limit0)) return;
+    for (int j = 0; j < 32; ++j) lo[j] = -__uint_as_float(r[j]);
+    issue_next();
 
     // sign of (limit - lo) shifted in column by column: column 0 ends in the top bit, a clear bit is a hit (lo <= limit)
     uint32_t mq[4] = {0u, 0u, 0u, 0u};                   // four independent chains of 8 columns
@@ -275,18 +288,13 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t nbs
 // First pass of a two-pass tile: every column's upper bound goes through the branch-free insertion network, so that the
 // threshold is already tight when the hits are collected (scan_chunk<.., false> over the same accumulators).
 template <int K>
-__device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, float C, float (&u)[K]) {
+__device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t p_c, float C, float (&u)[K]) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        const uint4 nb = lds_v4(nbs_c + 16u * g);
         const uint4 pp = lds_v4(p_c + 16u * g);
-        const float nbv[4] = {__uint_as_float(nb.x), __uint_as_float(nb.y), __uint_as_float(nb.z), __uint_as_float(nb.w)};
         const float ppv[4] = {__uint_as_float(pp.x), __uint_as_float(pp.y), __uint_as_float(pp.z), __uint_as_float(pp.w)};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float lo = fmaf(-C, ppv[i], nbv[i] - __uint_as_float(r[4 * g + i]));
-            upper_insert<K>(u, fmaf(2.0f * C, ppv[i], lo));
-        }
+        for (int i = 0; i < 4; ++i) upper_insert<K>(u, fmaf(2.0f * C, ppv[i], -__uint_as_float(r[4 * g + i])));
     }
 }
 
@@ -295,7 +303,7 @@ __device__ __forceinline__ void bound_chunk(const uint32_t (&r)[32], uint32_t nb
 // would be a hit; instead all 128 upper bounds go through the insertion network first and the hits are collected in a second
 // sweep over the same accumulators (they stay in tensor memory until the set is released).
 template <int K, int CAP, bool TWO_PASS, bool LABELLED>
-__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float Cpm,
+__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t p_addr, int col0, int n_class, float C,
                                           uint32_t cand_addr, int first, float (&u)[K], int &cnt, uint32_t &flags, float (&drop_lo)[2]) {
     uint32_t ra[32], rb[32];
     __syncwarp();                                      // tcgen05.ld is .sync.aligned: the warp must be converged
@@ -303,63 +311,33 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
     tmem_wait_ld();
     if (TWO_PASS) {
         tmem_ld32_issue(taddr + 32u, rb);
-        bound_chunk<K>(ra, nbs_addr, p_addr, C, u);
+        bound_chunk<K>(ra, p_addr, C, u);
         tmem_wait_ld();
         tmem_ld32_issue(taddr + 64u, ra);
-        bound_chunk<K>(rb, nbs_addr + 128u, p_addr + 128u, C, u);
+        bound_chunk<K>(rb, p_addr + 128u, C, u);
         tmem_wait_ld();
         tmem_ld32_issue(taddr + 96u, rb);
-        bound_chunk<K>(ra, nbs_addr + 256u, p_addr + 256u, C, u);
+        bound_chunk<K>(ra, p_addr + 256u, C, u);
         tmem_wait_ld();
         tmem_ld32_issue(taddr, ra);
-        bound_chunk<K>(rb, nbs_addr + 384u, p_addr + 384u, C, u);
+        bound_chunk<K>(rb, p_addr + 384u, C, u);
         tmem_wait_ld();
     }
     // The four chunks run through TWO copies of the scan code (a rolled loop over chunk pairs), not four.  With four inlined copies the
     // kernel had 15 700 instructions and a fifth of the epilogue's issue slots was lost to instruction fetch (ncu: stall_no_inst 18 %);
-    // measured on 1 M contigs x 4510 references: 3.09 -> 2.84 ms.  A single copy (the next chunk loaded into the registers the scan has
-    // just consumed, PHM_SCAN_COPIES 1) shortens the window in which the tensor-memory load overlaps the scan and measures 2.87 ms.
-#ifndef PHM_SCAN_COPIES
-#define PHM_SCAN_COPIES 2
-#endif
-#if PHM_SCAN_COPIES == 1
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        auto next = [&]() { if (c < 3) tmem_ld32_issue(taddr + 32u * (uint32_t)(c + 1), ra); };
-        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 128u * (uint32_t)c, p_addr + 128u * (uint32_t)c, col0 + 32 * c, n_class, C, Cpm,
-                                                 cand_addr, first, u, cnt, flags, drop_lo, next);
-        __syncwarp();
-        if (c < 3) tmem_wait_ld();
-    }
-#elif PHM_SCAN_COPIES == 2
+    // measured on 1 M contigs x 4510 references: 3.09 -> 2.84 ms.
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
         tmem_ld32_issue(taddr + 64u * (uint32_t)h + 32u, rb);
-        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u * (uint32_t)h, p_addr + 256u * (uint32_t)h, col0 + 64 * h, n_class, C, Cpm,
-                                                 cand_addr, first, u, cnt, flags, drop_lo);
+        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, p_addr + 256u * (uint32_t)h, col0 + 64 * h, n_class, C, cand_addr, first, u, cnt, flags, drop_lo);
         __syncwarp();
         tmem_wait_ld();
         if (h == 0) tmem_ld32_issue(taddr + 64u, ra);
-        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 256u * (uint32_t)h + 128u, p_addr + 256u * (uint32_t)h + 128u, col0 + 64 * h + 32, n_class,
-                                                 C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
+        scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, p_addr + 256u * (uint32_t)h + 128u, col0 + 64 * h + 32, n_class, C, cand_addr, first, u, cnt,
+                                                 flags, drop_lo);
         __syncwarp();
         if (h == 0) tmem_wait_ld();
     }
-#else
-    tmem_ld32_issue(taddr + 32u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr, p_addr, col0, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
-    __syncwarp();
-    tmem_wait_ld();
-    tmem_ld32_issue(taddr + 64u, ra);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
-    __syncwarp();
-    tmem_wait_ld();
-    tmem_ld32_issue(taddr + 96u, rb);
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
-    __syncwarp();
-    tmem_wait_ld();
-    scan_chunk<K, CAP, !TWO_PASS, LABELLED>(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, Cpm, cand_addr, first, u, cnt, flags, drop_lo);
-#endif
 }
 
 // ---------------- list mode: second pass over the rows whose candidate buffer overflowed ----------------
@@ -370,36 +348,11 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t nbs_addr, uin
 // prefix sum (tc_list_scan_kernel) gives every row its range in one shared pool, then the same pass FILLS the ranges
 // (cols != nullptr).  Lists are usually short (the interval is ~1 % of the distance) but a contig far from every reference
 // can have thousands of references inside it; only rows that do not fit in the pool go to the exhaustive kernels.
-__device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs_c, uint32_t p_c, int col_c, int n_class, float C, float Cpm,
-                                           float T, uint32_t *cnt, uint32_t *cols) {
-    float lo[32], gm[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {                                        // quick reject with the per-row constant, as in scan_chunk
-        const uint4 nb = lds_v4(nbs_c + 16u * g);
-        lo[4 * g + 0] = __uint_as_float(nb.x) - __uint_as_float(r[4 * g + 0]);
-        lo[4 * g + 1] = __uint_as_float(nb.y) - __uint_as_float(r[4 * g + 1]);
-        lo[4 * g + 2] = __uint_as_float(nb.z) - __uint_as_float(r[4 * g + 2]);
-        lo[4 * g + 3] = __uint_as_float(nb.w) - __uint_as_float(r[4 * g + 3]);
-        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
-    }
-    {
-        const float m0 = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-        if (!__any_sync(FULL, __fsub_rd(m0, Cpm) <= T)) return;
-    }
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const uint4 pp = lds_v4(p_c + 16u * g);
-        lo[4 * g + 0] = fmaf(-C, __uint_as_float(pp.x), lo[4 * g + 0]);
-        lo[4 * g + 1] = fmaf(-C, __uint_as_float(pp.y), lo[4 * g + 1]);
-        lo[4 * g + 2] = fmaf(-C, __uint_as_float(pp.z), lo[4 * g + 2]);
-        lo[4 * g + 3] = fmaf(-C, __uint_as_float(pp.w), lo[4 * g + 3]);
-        gm[g] = fminf(fminf(lo[4 * g + 0], lo[4 * g + 1]), fminf(lo[4 * g + 2], lo[4 * g + 3]));
-    }
-    const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-    if (!__any_sync(FULL, m <= T)) return;
+__device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], int col_c, int n_class, float T, uint32_t *cnt, uint32_t *cols) {
+    if (!__any_sync(FULL, -max32(r) <= T)) return;
     uint32_t hits = 0u;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) hits |= (lo[j] <= T ? 1u : 0u) << j;
+    for (int j = 0; j < 32; ++j) hits |= (-__uint_as_float(r[j]) <= T ? 1u : 0u) << j;
     const int real = n_class - col_c;                    // columns of this chunk that are references (the rest is padding)
     if (real < 32) hits &= real <= 0 ? 0u : ((1u << real) - 1u);
     while (hits) {
@@ -410,25 +363,24 @@ __device__ __forceinline__ void list_chunk(const uint32_t (&r)[32], uint32_t nbs
     }
 }
 
-__device__ __forceinline__ void list_tile(uint32_t taddr, uint32_t nbs_addr, uint32_t p_addr, int col0, int n_class, float C, float Cpm, float T,
-                                          uint32_t *cnt, uint32_t *cols) {
+__device__ __forceinline__ void list_tile(uint32_t taddr, int col0, int n_class, float T, uint32_t *cnt, uint32_t *cols) {
     uint32_t ra[32], rb[32];
     __syncwarp();
     tmem_ld32_issue(taddr, ra);
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 32u, rb);
-    list_chunk(ra, nbs_addr, p_addr, col0, n_class, C, Cpm, T, cnt, cols);
+    list_chunk(ra, col0, n_class, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 64u, ra);
-    list_chunk(rb, nbs_addr + 128u, p_addr + 128u, col0 + 32, n_class, C, Cpm, T, cnt, cols);
+    list_chunk(rb, col0 + 32, n_class, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
     tmem_ld32_issue(taddr + 96u, rb);
-    list_chunk(ra, nbs_addr + 256u, p_addr + 256u, col0 + 64, n_class, C, Cpm, T, cnt, cols);
+    list_chunk(ra, col0 + 64, n_class, T, cnt, cols);
     __syncwarp();
     tmem_wait_ld();
-    list_chunk(rb, nbs_addr + 384u, p_addr + 384u, col0 + 96, n_class, C, Cpm, T, cnt, cols);
+    list_chunk(rb, col0 + 96, n_class, T, cnt, cols);
 }
 
 struct TcParams {
@@ -437,6 +389,8 @@ struct TcParams {
     int nt_ref, nt_pos, nt_neg;          // column tiles of each class (each class padded to a multiple of 128 rows)
     int n_refs, n_cent_pos, n_cent_neg;  // real columns of each class
     const __half *b_img;                 // reference operand, one 16 KB shared-memory image per (tile, K chunk)
+    const __half *bx_img;                // extra K columns of the references, one 4 KB no-swizzle image per tile
+    const __half *ax_img;                // extra K columns of the query rows, one 4 KB no-swizzle image per 128 rows
     const float *nbs;                    // [(nt_ref + nt_pos + nt_neg) * 128] 2^23 |b'|^2, PAD_NORM on padding rows
     const float *pnorm;                  // same layout: P_j = |B~_j| rounded up, 0 on padding rows
     const float *crow;                   // [n_points] C_row (NaN for a NaN feature row)
@@ -537,11 +491,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                                   bar_b_full + 8 * bstage);
                         if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
                     }
-                    // |b|^2 and P of this tile for the epilogue, once the epilogue has let go of the set (two tiles ago)
+                    {
+                        // fifth slot of the tile: the extra K columns -- the tile's references, then the two row blocks of the contig tile
+                        mbar_wait(bar_b_empty + 8 * bstage, bphase ^ 1u);
+                        mbar_expect_tx(bar_b_full + 8 * bstage, 3 * XBLK_BYTES);
+                        const uint32_t slot = sm_b + bstage * BLOCK_BYTES;
+                        bulk_load(slot, p.bx_img + (int64_t)nt * XBLK_HALVES, XBLK_BYTES, bar_b_full + 8 * bstage);
+                        bulk_load(slot + XBLK_BYTES, p.ax_img + (int64_t)(2 * mt) * XBLK_HALVES, 2 * XBLK_BYTES, bar_b_full + 8 * bstage);
+                        if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
+                    }
+                    // P of this tile for the epilogue's hits, once the epilogue has let go of the set (two tiles ago)
                     const uint32_t set = tile & 1u;
                     mbar_wait(bar_t_empty + 8 * set, ((tile >> 1) & 1u) ^ 1u);
-                    mbar_expect_tx(bar_n_full + 8 * set, 2 * BN * 4);
-                    bulk_load(sm_stg + set * (2 * BN * 4), p.nbs + (int64_t)nt * BN, BN * 4, bar_n_full + 8 * set);
+                    mbar_expect_tx(bar_n_full + 8 * set, BN * 4);
                     bulk_load(sm_stg + set * (2 * BN * 4) + BN * 4, p.pnorm + (int64_t)nt * BN, BN * 4, bar_n_full + 8 * set);
                 }
             }
@@ -580,7 +542,21 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                             }
                         }
                         umma_commit(bar_b_empty + 8 * bstage);    // block reusable once these MMAs have read it
-                        if (kc == NKC - 1) umma_commit(bar_t_full + 8 * set);            // accumulator set complete
+                    }
+                    __syncwarp();
+                    if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
+                }
+                {
+                    // the seventeenth k-step: accumulator += (2^10, 2^-1, 2^-12, C16) . (-n1, -n2, -n3, P16)
+                    mbar_wait(bar_b_full + 8 * bstage, bphase);
+                    tc_fence_after();
+                    const uint32_t slot = sm_b + bstage * BLOCK_BYTES;
+                    if (elect_one()) {
+                        const uint64_t xb = smem_desc_plain(slot);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) umma_f16(tmem_d + h * BN, smem_desc_plain(slot + XBLK_BYTES + h * XBLK_BYTES), xb, 1u);
+                        umma_commit(bar_b_empty + 8 * bstage);
+                        umma_commit(bar_t_full + 8 * set);            // accumulator set complete
                     }
                     __syncwarp();
                     if (++bstage == NSTAGE) { bstage = 0; bphase ^= 1u; }
@@ -599,11 +575,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
         for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
             const int mt = item / sched.n_slices;
             const int64_t row = (int64_t)mt * MT + row_in_tile;
-            float C = (row < sched.n_rows) ? p.crow[row] : NAN;
+            float C = (row < sched.n_rows) ? c16_up(p.crow[row]) : NAN;   // the value the extra K column carries (rounded up to FP16)
             const bool live = C >= 0.0f;                           // false for padding rows and NaN feature rows
             const float init = live ? INFINITY : -INFINITY;        // -inf: nothing ever qualifies
             if (!live) C = 0.0f;
-            const float Cpm = __fmul_ru(C, p.consts->pmax);        // quick-reject constant of scan_chunk
             if constexpr (LIST) {
                 const int sl = item - mt * sched.n_slices;
                 const int nt_lo = (int)((long long)p.nt_ref * sl / sched.n_slices), nt_hi = (int)((long long)p.nt_ref * (sl + 1) / sched.n_slices);
@@ -622,7 +597,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                     mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
-                    list_tile(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, Cpm, T, my_cnt, my_cols);
+                    list_tile(taddr, nt * BN, p.n_refs, T, my_cnt, my_cols);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -645,17 +620,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
                 if (p.skip_scan) {
                 } else if (nt == 0)
-                    scan_tile<KN, CAP_R, true, true>(taddr, stg, stg + BN * 4, 0, p.n_refs, C, Cpm, cand_addr, 0, ur, cnt_r, flags, drop_lo);
+                    scan_tile<KN, CAP_R, true, true>(taddr, stg + BN * 4, 0, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt < p.nt_ref)
-                    scan_tile<KN, CAP_R, false, true>(taddr, stg, stg + BN * 4, nt * BN, p.n_refs, C, Cpm, cand_addr, 0, ur, cnt_r, flags, drop_lo);
+                    scan_tile<KN, CAP_R, false, true>(taddr, stg + BN * 4, nt * BN, p.n_refs, C, cand_addr, 0, ur, cnt_r, flags, drop_lo);
                 else if (nt == p.nt_ref)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_pos, C, Cpm, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg + BN * 4, 0, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt < p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, Cpm, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg + BN * 4, (nt - p.nt_ref) * BN, p.n_cent_pos, C, cand_addr, CAP_R, up, cnt_p, flags, drop_lo);
                 else if (nt == p.nt_ref + p.nt_pos)
-                    scan_tile<1, CAP_C, true, false>(taddr, stg, stg + BN * 4, 0, p.n_cent_neg, C, Cpm, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
+                    scan_tile<1, CAP_C, true, false>(taddr, stg + BN * 4, 0, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 else
-                    scan_tile<1, CAP_C, false, false>(taddr, stg, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, Cpm, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
+                    scan_tile<1, CAP_C, false, false>(taddr, stg + BN * 4, (nt - p.nt_ref - p.nt_pos) * BN, p.n_cent_neg, C, cand_addr, CAP_R + CAP_C, un, cnt_n, flags, drop_lo);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * set);
@@ -727,7 +702,7 @@ __device__ __forceinline__ void load_query_row(const double *points, const uint3
 __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c,
                                     const uint32_t *__restrict__ src_counts, int is_ref, int64_t n_positive, __half *__restrict__ op, double *__restrict__ norm64, double *__restrict__ cnorm64,
                                     float *__restrict__ nbs, float *__restrict__ pnorm, float *__restrict__ crow,
-                                    PrepConsts *consts, uint32_t *__restrict__ row_total) {
+                                    PrepConsts *consts, uint32_t *__restrict__ row_total, __half *__restrict__ bx) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -761,10 +736,37 @@ __global__ void tc_prep_rows_kernel(const double *__restrict__ src, int64_t n_sr
             const double dB = sqrt(sd) * (1.0 + 1e-12);
             const double nH = sqrt(sh) * (1.0 + 1e-12);
             if (is_ref) {
-                nbs[r] = real ? (float)(sc * NORM_SCALE) : PAD_NORM;
-                // P rounded up, bumped past the next even pattern, label (source row < n_positive) in the lowest mantissa bit
-                const uint32_t pb = ((__float_as_uint(float_up(P)) + 2u) & ~1u) | (uint32_t)(sr < n_positive);
+                const float nb = real ? (float)(sc * NORM_SCALE) : PAD_NORM;
+                nbs[r] = nb;
+                // the extra K columns of this reference (see XK): three-way FP16 split of nbs (exact), P rounded UP to FP16
+                __half p16 = __float2half_ru(float_up(P));
+                __half n1 = __float2half_rn(65504.0f), n2 = n1, n3 = n1;           // padding rows: lower bound +6.7e7, never a hit
+                if (real) {
+                    n1 = __float2half_rn(nb * (1.0f / 1024.0f));
+                    const float r1 = fmaf(-1024.0f, __half2float(n1), nb);         // exact: nb has 24 bits, n1 takes the top 11
+                    n2 = __float2half_rn(r1 * 2.0f);
+                    const float r2 = fmaf(-0.5f, __half2float(n2), r1);
+                    n3 = __float2half_rn(r2 * 4096.0f);
+                    const float left = fmaf(-1.0f / 4096.0f, __half2float(n3), r2);
+                    // a reference within 1e-6 of the uniform vector would need FP16 subnormals below 2^-24 for its third piece:
+                    // give it the widest interval FP16 can carry instead (always a candidate, measured exactly)
+                    if (left != 0.0f || __hisinf(n1)) p16 = __float2half_rn(65504.0f);
+                } else {
+                    p16 = __float2half_rn(0.0f);
+                }
+                // P as the epilogue uses it for upper bounds: the FP16 value (or a hair more), label (source row < n_positive) in the
+                // lowest mantissa bit
+                const uint32_t pb = (__float_as_uint(__half2float(p16)) & ~1u) | (uint32_t)(sr < n_positive);
                 pnorm[r] = real ? __uint_as_float(pb) : 0.0f;
+                {
+                    const __half hz = __float2half_rn(0.0f);
+                    const __half row16[8] = {__hneg(n1), __hneg(n2), __hneg(n3), p16, hz, hz, hz, hz};
+                    uint4 v;
+                    memcpy(&v, row16, 16);
+                    uint4 *dst = reinterpret_cast<uint4 *>(bx + xrow_offset(r));
+                    dst[0] = v;
+                    dst[8] = make_uint4(0u, 0u, 0u, 0u);                            // K half 1: 128 bytes further
+                }
                 if (real && P > 0.0) {
                     atomicMax(reinterpret_cast<int *>(&consts->rho), __float_as_int(float_up((dB + EPS_ACC * (P + dB)) / P)));
                     atomicMax(reinterpret_cast<int *>(&consts->pmax), __float_as_int(float_up(P)));
@@ -1097,11 +1099,28 @@ __global__ void __launch_bounds__(256, PHM_DECIDE_MIN_CTAS) score_decide_kernel(
     }
 }
 
+// ---------------- extra K columns of the query rows: (2^10, 2^-1, 2^-12, C16, 0 ...) per row, from the row's error constant ----------------
+__device__ __forceinline__ void write_ax_row(__half *ax, int64_t row, float c) {
+    const bool live = c >= 0.0f;                                       // NaN (empty contig) and padding rows: C = 0, the row keeps nothing anyway
+    const __half row16[8] = {__float2half_rn(1024.0f), __float2half_rn(0.5f), __float2half_rn(1.0f / 4096.0f),
+                             live ? __float2half_ru(c) : __float2half_rn(0.0f),
+                             __float2half_rn(0.0f), __float2half_rn(0.0f), __float2half_rn(0.0f), __float2half_rn(0.0f)};
+    uint4 v;
+    memcpy(&v, row16, 16);
+    uint4 *dst = reinterpret_cast<uint4 *>(ax + xrow_offset(row));
+    dst[0] = v;
+    dst[8] = make_uint4(0u, 0u, 0u, 0u);                               // K half 1
+}
+__global__ void __launch_bounds__(256) tc_build_ax_kernel(const float *__restrict__ crow, int64_t n, int64_t n_pad, __half *__restrict__ ax) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_pad; row += (int64_t)gridDim.x * blockDim.x)
+        write_ax_row(ax, row, row < n ? crow[row] : NAN);
+}
+
 // ---------------- list pass: compaction of its rows, and the exact decision over the listed references ----------------
 __global__ void __launch_bounds__(256) tc_list_gather_kernel(const __half *__restrict__ a_op, const float *__restrict__ crow,
                                                              const int64_t *__restrict__ list_rows, const unsigned long long *list_count,
                                                              int max_rows, __half *__restrict__ a_list, float *__restrict__ crow_list,
-                                                             uint32_t *__restrict__ list_cnt) {
+                                                             uint32_t *__restrict__ list_cnt, __half *__restrict__ ax_list) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1117,7 +1136,7 @@ __global__ void __launch_bounds__(256) tc_list_gather_kernel(const __half *__res
             c = crow[row];
         }
         reinterpret_cast<uint4 *>(a_list)[slot * (KDIM * 2 / 16) + lane] = v;
-        if (lane == 0) { crow_list[slot] = c; list_cnt[slot] = 0u; }
+        if (lane == 0) { crow_list[slot] = c; list_cnt[slot] = 0u; write_ax_row(ax_list, slot, c); }
     }
 }
 
@@ -1565,6 +1584,7 @@ struct TcWorkspace {
     int64_t list_pool_entries;
     int64_t *list_rows; float *list_thr; double *list_km; float *list_crow; uint32_t *list_cnt, *list_n, *list_off, *list_cols; __half *a_list;
     __half *a_op, *b_op;
+    __half *ax_img, *bx_img, *ax_list;            // extra K columns (XK per row, no-swizzle 128-row images)
     float *nbs, *pnorm, *crow;
     uint2 *cand; float *cand_up; uint32_t *meta; float2 *drop_lo; float *thr_out;
     double *norm_points, *norm_refs, *norm_cpos, *norm_cneg;
@@ -1589,6 +1609,8 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     w.consts = reinterpret_cast<PrepConsts *>(head + 192);
     w.a_op = reinterpret_cast<__half *>(take((size_t)n * KDIM * 2));
     w.b_op = reinterpret_cast<__half *>(take((size_t)r_pad * KDIM * 2));
+    w.bx_img = reinterpret_cast<__half *>(take((size_t)r_pad * XK * 2));
+    w.ax_img = reinterpret_cast<__half *>(take((size_t)round_up(n > 0 ? n : 1, MT) * XK * 2));
     w.nbs = reinterpret_cast<float *>(take((size_t)r_pad * 4));
     w.pnorm = reinterpret_cast<float *>(take((size_t)r_pad * 4));
     w.crow = reinterpret_cast<float *>(take((size_t)n * 4));
@@ -1619,6 +1641,7 @@ static TcWorkspace carve_tc(void *ws, int64_t n, int64_t r_pad, int64_t n_refs, 
     if (w.list_pool_entries < ((int64_t)1 << 22)) w.list_pool_entries = (int64_t)1 << 22;
     w.list_cols = reinterpret_cast<uint32_t *>(take((size_t)w.list_pool_entries * 4));
     w.a_list = reinterpret_cast<__half *>(take((size_t)lmax * KDIM * 2));
+    w.ax_list = reinterpret_cast<__half *>(take((size_t)lmax * XK * 2));
     w.bytes = off;
     return w;
 }
@@ -1634,12 +1657,12 @@ bool score_tc_supported(int dim, int k_neighbors, int64_t n_refs, int64_t n_cp, 
 
 static int launch_prep(const double *src, const uint32_t *src_counts, int64_t n_src, int64_t n_rows, int64_t perm_a, int64_t perm_c, int is_ref, int64_t n_positive, __half *op,
                        double *norm64, double *cnorm64, float *nbs, float *pnorm, float *crow, PrepConsts *consts, cudaStream_t st,
-                       uint32_t *row_total = nullptr) {
+                       uint32_t *row_total = nullptr, __half *bx = nullptr) {
     if (n_rows == 0) return PHM_OK;
     int64_t blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     tc_prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_src, n_rows, perm_a, perm_c, src_counts, is_ref, n_positive, op, norm64, cnorm64, nbs, pnorm,
-                                                          crow, consts, row_total);
+                                                          crow, consts, row_total, bx);
     PHM_LAUNCH_CHECK();
     return PHM_OK;
 }
@@ -1694,11 +1717,13 @@ int score_tc_begin(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t s
     int rc;
     int64_t perm_a, perm_c;
     ref_permutation(a.n_refs, &perm_a, &perm_c);
-    if ((rc = launch_prep(a.refs, nullptr, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st)) != PHM_OK) return rc;
+    if ((rc = launch_prep(a.refs, nullptr, a.n_refs, ref_pad, perm_a, perm_c, 1, a.n_positive, w.b_op, w.norm_refs, nullptr, w.nbs, w.pnorm, nullptr, w.consts, st,
+                          nullptr, w.bx_img)) != PHM_OK) return rc;
     if ((rc = launch_prep(a.cent_pos, nullptr, a.n_cent_pos, cp_pad, 1, 0, 1, 0, w.b_op + ref_pad * KDIM, w.norm_cpos, nullptr, w.nbs + ref_pad,
-                          w.pnorm + ref_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
+                          w.pnorm + ref_pad, nullptr, w.consts, st, nullptr, w.bx_img + ref_pad * XK)) != PHM_OK) return rc;
     if ((rc = launch_prep(a.cent_neg, nullptr, a.n_cent_neg, cn_pad, 1, 0, 1, 0, w.b_op + (ref_pad + cp_pad) * KDIM, w.norm_cneg, nullptr,
-                          w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st)) != PHM_OK) return rc;
+                          w.nbs + ref_pad + cp_pad, w.pnorm + ref_pad + cp_pad, nullptr, w.consts, st, nullptr,
+                          w.bx_img + (ref_pad + cp_pad) * XK)) != PHM_OK) return rc;
     if (emit) { emit->op = w.a_op; emit->crow = w.crow; emit->cnorm = w.cnorm_points; emit->total = w.row_total; emit->consts = w.consts; }
     return PHM_OK;
 }
@@ -1732,6 +1757,14 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     p.n_mtiles = (int)((n + MT - 1) / MT);
     p.nt_ref = (int)(ref_pad / BN); p.nt_pos = (int)(cp_pad / BN); p.nt_neg = (int)(cn_pad / BN);
     p.n_refs = (int)a.n_refs; p.n_cent_pos = (int)a.n_cent_pos; p.n_cent_neg = (int)a.n_cent_neg;
+    {
+        const int64_t n_pad = round_up(n, MT);
+        int64_t blocks = (n_pad + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+        tc_build_ax_kernel<<<(unsigned)blocks, 256, 0, st>>>(w.crow, n, n_pad, w.ax_img);
+        PHM_LAUNCH_CHECK();
+    }
+    p.bx_img = w.bx_img; p.ax_img = w.ax_img;
     p.b_img = w.b_op; p.nbs = w.nbs; p.pnorm = w.pnorm; p.crow = w.crow; p.consts = w.consts; p.cand = w.cand; p.cand_up = w.cand_up; p.meta = w.meta; p.drop_lo = w.drop_lo; p.thr_out = w.thr_out;
     p.ref_pad = (int)ref_pad; p.cp_pad = (int)cp_pad;
     p.skip_scan = score_force_fallback;
@@ -1768,12 +1801,14 @@ int score_tc_finish(const ScoreArgs &a, void *ws, size_t ws_bytes, cudaStream_t 
     // rows whose candidate buffer overflowed but whose threshold is final: second tensor-core pass that lists every reference
     // under the threshold, then the exact decision over the lists (row count read on the device: no host synchronisation)
     if (use_list) {
-        tc_list_gather_kernel<<<sm_count(), 256, 0, st>>>(w.a_op, w.crow, w.list_rows, w.list_count, w.list_max_rows, w.a_list, w.list_crow, w.list_cnt);
+        tc_list_gather_kernel<<<sm_count(), 256, 0, st>>>(w.a_op, w.crow, w.list_rows, w.list_count, w.list_max_rows, w.a_list, w.list_crow, w.list_cnt,
+                                                          w.ax_list);
         PHM_LAUNCH_CHECK();
         CUtensorMap map_list;
         if ((rc = make_map(&map_list, w.a_list, w.list_max_rows)) != PHM_OK) return rc;
         TcParams pl = p;
         pl.crow = w.list_crow;
+        pl.ax_img = w.ax_list;
         for (int pass = 0; pass < 2; ++pass) {                           // count, prefix sum, fill
             pl.list_cols = pass ? w.list_cols : nullptr;
             switch (a.k_neighbors) {
