@@ -593,8 +593,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, TcParams p) {
                 for (int nt = nt_lo; nt < nt_hi; ++nt, ++tile) {
                     const uint32_t set = tile & 1u;
                     const uint32_t stg = sm_stg + set * (2 * BN * 4);
-                    mbar_wait(bar_n_full + 8 * set, (tile >> 1) & 1u);
                     mbar_wait(bar_t_full + 8 * set, (tile >> 1) & 1u);
+                    mbar_wait(bar_n_full + 8 * set, (tile >> 1) & 1u);      // P of the tile (hits only): issued with the MMAs, long there by now
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2 * BN) + half * BN;
                     list_tile(taddr, nt * BN, p.n_refs, T, my_cnt, my_cols);
