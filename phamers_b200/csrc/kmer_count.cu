@@ -390,11 +390,23 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
                     const int ch = it * 32 + lane;
                     return (ch < nchunks) ? ldg_stream(gp + ch) : make_uint4(0u, 0u, 0u, 0u);
                 };
+                // chunks ch_lo .. ch_lo + span - 1 lie wholly inside the range: ONE unsigned comparison tells an edge chunk (or one past
+                // the end), and edge chunks and chunks with a byte that is not a symbol share one rare branch
+                const int ch_lo = startrel ? 1 : 0;
+                const unsigned span = (endrel >> 4) > ch_lo ? (unsigned)((endrel >> 4) - ch_lo) : 0u;
                 auto decode = [&](uint4 raw, int it) -> Dec {          // exact blank mask, range boundaries included
                     const int ch = it * 32 + lane;
-                    if (ch >= nchunks) return Dec{0u, 0xFFFFFFFFu};
-                    const int pos = ch << 4;
-                    return decode_chunk(raw, startrel - pos, endrel - pos, inv);
+                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+                    Dec d;
+                    d.s = codes16_be(w);
+                    d.blank = 0u;
+                    const bool edge = (unsigned)(ch - ch_lo) >= span;
+                    if (edge | (any_invalid16(w) != 0u)) {
+                        if (ch >= nchunks) return Dec{0u, 0xFFFFFFFFu};
+                        if (any_invalid16(w)) { d.blank = blank_mask16_be(w); inv = 1u; }
+                        if (edge) d.blank |= outside_mask16_be(startrel - (ch << 4), endrel - (ch << 4));
+                    }
+                    return d;
                 };
                 // the windows of one step on the clean path / with per-base blank masks
                 auto post_clean = [&](uint32_t cur_s, uint32_t hi_s) {
