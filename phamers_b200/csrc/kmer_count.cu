@@ -282,6 +282,20 @@ __device__ __forceinline__ void red_global_add(uint32_t *p, uint32_t v) {
 // the re-arm; the register ring stays the default.
 constexpr int STAGE_BYTES = 512;
 
+// EXPERIMENT, OFF (compile with -DPHM_HIST_DESKEW=1).  The bank of a 5-mer counter is the low five bits of its index: the last 2.5
+// bases of the window.  A contig's GC content is anywhere between 25 % and 75 %, so the "G or C" (high) bits of bases 3 and 4 are
+// biased and the 32 lanes of an atomic pile up on fewer banks: expected conflict degree 3.9 over the workload against 3.53 for uniform
+// banks (simulation and ncu agree).  XOR-ing those two bits with the LOW bits of bases 0 and 1 -- fair coins under Chargaff's second
+// rule, and independent of bases 3 and 4 -- makes all five bank bits fair and independent.  Index bit 3 ^= bit 8, bit 1 ^= bit 6 (a
+// bijection of the table onto itself); on byte offsets: off ^ ((off >> 5) & 0x28).  The fold reads row y ^ 2 * (y >> 6 & 1) for bin y
+// and swaps the word pairs of a row when y's bit 4 is set.  Bit-exact on every test -- and SLOWER: 5.21 against 4.88 ms per 1 M
+// contigs.  The two extra instructions per atomic (16 per step) cost more than the 0.4 wavefronts per atomic they save; a per-chunk
+// scramble of the stream cannot do it, because windows overlap and a window's index must not depend on bases outside it.
+#ifndef PHM_HIST_DESKEW
+#define PHM_HIST_DESKEW 0
+#endif
+__device__ __forceinline__ uint32_t deskew_off(uint32_t off) { return off ^ ((off >> 5) & 0x28u); }
+
 struct HistJob {
     const uint8_t *seq; const int64_t *off; int64_t n_contigs;
     uint32_t *counts; double *freq;
@@ -298,6 +312,7 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
     using Cfg = HistCfg<K, STRIDE>;
     constexpr int W = Cfg::W;
     constexpr bool FUSED = (K == 4 && STRIDE == 2);          // fold and clear of the 5-mer table in one pass
+    constexpr bool DESKEW = FUSED && (PHM_HIST_DESKEW != 0); // 5-mer table with de-skewed bank bits (deskew_off)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint8_t *__restrict__ seq = job.seq;
     uint32_t *__restrict__ counts = job.counts;
@@ -416,7 +431,7 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
                             post6(tab, window_raw<6>(cur_s, hi_s, p, 1));
                         } else {
                             const uint32_t woff = window_offset<W>(cur_s, hi_s, p);
-                            red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : woff));
+                            red_shared_inc(tab | (SWZ ? swz_off<K>(woff) : (DESKEW ? deskew_off(woff) : woff)));
                         }
                     }
                 };
@@ -427,7 +442,7 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
                         const uint32_t idx = window_bits<W>(cur.s, hi_s, p);
                         if (bl == 0u) {
                             if (Cfg::PACKED) post6(tab, idx << 1);
-                            else red_shared_inc(tab + (SWZ ? swz_off<K>(4u * idx) : 4u * idx));
+                            else red_shared_inc(tab + (SWZ ? swz_off<K>(4u * idx) : (DESKEW ? deskew_off(4u * idx) : 4u * idx)));
                         } else if (STRIDE > 1) {
                             // a partly blank window still holds up to STRIDE clean k-mers
 #pragma unroll
@@ -526,11 +541,20 @@ kmer_hist_kernel(const __grid_constant__ HistJob job, const __grid_constant__ tc
                 s2[0] = make_uint4(0u, 0u, 0u, 0u); s2[1] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint32_t a = tab + 16u * (uint32_t)(lane + 32 * i);
+                    // de-skewed table: bin y = lane + 32 i lives in row y ^ 2 * (bit 6 of y) = (lane ^ 2 * (i >> 1 & 1)) + 32 i
+                    const uint32_t a = tab + 16u * (uint32_t)((DESKEW ? (lane ^ (((i >> 1) & 1) << 1)) : lane) + 32 * i);
                     const uint4 q = lds_v4(a);
                     sts_v4_zero(a);
                     vreg[i] = q.x + q.y + q.z + q.w;
                     s2[i & 1].x += q.x; s2[i & 1].y += q.y; s2[i & 1].z += q.z; s2[i & 1].w += q.w;
+                }
+                if (DESKEW && (lane & 16)) {
+                    // ... and the fifth base's high bit is flipped in the rows of bins with bit 4 set (all of this lane's, or none)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint4 t = s2[h];
+                        s2[h] = make_uint4(t.z, t.w, t.x, t.y);
+                    }
                 }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
