@@ -272,15 +272,24 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], uint32_t p_c
             cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], m, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
         }
     }
-    uint32_t todo = __reduce_or_sync(FULL, n_hits > 1 ? hits : 0u);
-    while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const float lo_j = pick32(lo, j);
-        if (n_hits > 1 && ((hits >> j) & 1u) && lo_j <= u[K - 1] && col_c + j < n_class) {
-            const uint32_t pbits = lds_u32(p_c + 4u * j);
-            if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), lo_j));
-            cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
+    // Lanes with several hits in the chunk walk their OWN hit bits (a divergent loop; the values come back from a thread-local copy
+    // of the 32 bounds, indexed dynamically).  Round 1 walked the union of all lanes' hit columns warp-uniformly -- up to 32 rounds
+    // in the tiles right after the first, where every row still has several hits per chunk -- and that, not the scan, was what kept
+    // an accumulator set from going back to the MMA warp.
+    uint32_t multi = n_hits > 1 ? hits : 0u;
+    if (__any_sync(FULL, multi != 0u)) {
+        float lo_mem[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo_mem[j] = lo[j];
+        while (multi) {
+            const int j = __ffs(multi) - 1;
+            multi &= multi - 1u;
+            const float lo_j = lo_mem[j];
+            if (lo_j <= u[K - 1] && col_c + j < n_class) {
+                const uint32_t pbits = lds_u32(p_c + 4u * j);
+                if (INSERT) upper_insert<K>(u, fmaf(2.0f * C, __uint_as_float(pbits), lo_j));
+                cand_append<CAP>(cand_addr, first, cnt, flags, drop_lo, u[K - 1], lo_j, col_c + j, LABELLED ? (int)(pbits & 1u) : -1);
+            }
         }
     }
 }
