@@ -210,7 +210,7 @@ int phm_score_stats(const void *d_workspace, uint64_t *fallback_rows, float *max
 
 /* Tuning / path selection for experiments and tests (defaults are the measured best; every variant gives the same results).
  * Options: "hist_stride_k4" (2 | 1: 5-mer windows at every second base | plain 4-mers), "hist_stride_k5" (0 = automatic | 1 | 2: 6-mer windows in 16-bit packed counters),
- * "hist_warps_k6" (13 | 4), "hist_canonical_swizzle" (1 | 0: bank-swizzled table for the canonical fold at k = 5, 6),
+ * "hist_warps_k5" (18 | 8: warps per CTA of the packed k = 5 table), "hist_warps_k6" (13 | 4), "hist_canonical_swizzle" (1 | 0: bank-swizzled table for the canonical fold at k = 5, 6),
  * "hist_tma" (0 | 1: sequence staged in shared memory by cp.async.bulk), "hist_plan" (1 | 0: records of 131 072 bases and more
  * are cut into tiles counted by different warps | every record is one work item),
  * "score_force_fallback" (1 = the first tensor-core pass keeps no candidate, so that every row takes the overflow road -- listing pass

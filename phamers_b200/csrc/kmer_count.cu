@@ -1024,6 +1024,7 @@ int hist_stride_for_k4 = 2;          // tuning knob (phm_set_option)
 int hist_stride_for_k5 = 0;          // 0 = automatic: 6-mers at every second base in 16-bit packed counters for plain bins (7.96 vs 8.22 ms),
                                      // plain 5-mers on the bank-swizzled table for canonical bins (7.70 vs 8.90 ms); 1 | 2 force one
 int hist_warps_k6 = 13;
+int hist_warps_k5 = 18;               // packed k = 5 table: one CTA of 18 warps per SM (7.79 ms) or 8 warps per CTA, 2 CTAs per SM (8.00)
 int hist_tma = 0;                    // 1 = sequence staged in shared memory by TMA bulk copies (k = 4, 5, 6)
 int hist_plan = 1;                   // 0 = no work plan: every contig is one item drawn in file order (round-1 scheduling)
 int hist_canonical_swizzle = 1;      // k = 5, 6 canonical: bank-swizzled table + shared-memory look-up table (0 = plain layout, for comparison)
@@ -1190,6 +1191,8 @@ extern "C" int phm_kmer_count(const uint8_t *d_seq, const int64_t *d_offsets, in
                                 : launch_hist<4, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w, st);
             return launch_hist<4, 1, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w, st);
         case 5:
+            if ((hist_stride_for_k5 == 2 || (hist_stride_for_k5 == 0 && !rc)) && hist_warps_k5 == 18)
+                return launch_hist<5, 2, 18>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w, st);
             if (hist_stride_for_k5 == 2 || (hist_stride_for_k5 == 0 && !rc))
                 return launch_hist<5, 2, 8>(d_seq, d_offsets, n_contigs, d_counts, d_freq, rc, canon, out_bins, w, st);
             if (rc && hist_canonical_swizzle)

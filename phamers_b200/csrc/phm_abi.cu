@@ -50,6 +50,7 @@ int max_smem_optin() {
 extern int hist_stride_for_k4;
 extern int hist_stride_for_k5;
 extern int hist_warps_k6;
+extern int hist_warps_k5;
 extern int hist_tma;
 extern int hist_canonical_swizzle;
 extern int hist_plan;
@@ -94,6 +95,7 @@ extern "C" int phm_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "hist_canonical_swizzle")) { hist_canonical_swizzle = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_plan")) { hist_plan = value != 0; return PHM_OK; }
     if (!strcmp(name, "hist_tma")) { hist_tma = value != 0; return PHM_OK; }
+    if (!strcmp(name, "hist_warps_k5")) { PHM_REQUIRE(value == 8 || value == 18, "8 or 18"); hist_warps_k5 = (int)value; return PHM_OK; }
     if (!strcmp(name, "hist_warps_k6")) { PHM_REQUIRE(value == 4 || value == 13, "4 or 13"); hist_warps_k6 = (int)value; return PHM_OK; }
     if (!strcmp(name, "score_path")) { PHM_REQUIRE(value >= 0 && value <= 2, "0 auto, 1 exact, 2 tensor cores"); score_path = (int)value; return PHM_OK; }
     if (!strcmp(name, "time_kernels")) { time_kernels = value != 0; return PHM_OK; }

@@ -238,6 +238,7 @@ def test_every_k4_window_stride_matches_oracle(stride):
 
 
 @pytest.mark.parametrize("k,option,value,default", [(5, "hist_stride_k5", 1, 0), (5, "hist_stride_k5", 2, 0),
+                                                     (5, "hist_warps_k5", 18, 18), (5, "hist_warps_k5", 8, 18),
                                                      (6, "hist_warps_k6", 4, 13), (6, "hist_warps_k6", 13, 13)])
 def test_k5_k6_kernel_variants_match_oracle(k, option, value, default):
     """k = 5 as plain 5-mers or as 6-mers at every second base in 16-bit packed counters (folded every 248 steps: the 300 kb contig
