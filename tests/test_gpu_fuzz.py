@@ -107,3 +107,84 @@ def test_random_rounds_fused_count_score(round_):
     two = ops.score_cuda(plain, scorer.refs, scorer.n_positive, scorer.cent_pos, scorer.cent_neg, 3)            # int32 counts in
     for a, b in zip((knn, km, combo), two):
         assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+
+
+def _scoring_case(rng):
+    """Random shapes and composition families: (reference counts, n_positive, query counts, centroid counts x 2, k)."""
+    n_fam = int(rng.integers(1, 9))
+    alpha = float(rng.choice([0.05, 0.3, 0.7, 3.0, 50.0]))
+    base = rng.dirichlet(np.full(256, alpha), size=n_fam)
+    if rng.random() < 0.3:
+        base[0] = np.full(256, 1.0 / 256)                               # the uniform composition: degenerate centred rows
+
+    def sample(n, depth):
+        fam = rng.integers(0, n_fam, size=n)
+        return np.stack([rng.multinomial(int(rng.integers(max(1, depth // 2), depth * 2)), base[f]) for f in fam]).astype(np.int64)
+
+    depth = int(rng.choice([60, 2000, 20000, 3000000]))
+    n_refs = int(rng.choice([3, 5, 127, 128, 129, 300, 1000, 2500]))
+    kn = int(rng.choice([1, 3, 5]))
+    n_refs = max(n_refs, kn)
+    n_pos = int(rng.integers(1, n_refs)) if n_refs > 1 else 1
+    n_pts = int(rng.choice([1, 31, 255, 256, 257, 600]))
+    n_cp, n_cn = int(rng.choice([1, 2, 86, 130])), int(rng.choice([1, 3, 86]))
+    ref_counts = sample(n_refs, depth)
+    ref_counts[ref_counts.sum(axis=1) == 0, 0] = 1                      # a reference row is never empty
+    if n_refs >= 8:
+        dup = rng.integers(0, n_refs, size=4)
+        ref_counts[dup[2:]] = ref_counts[dup[:2]]                       # duplicated references, possibly with opposite labels
+    q_counts = sample(n_pts, depth)
+    hit = rng.integers(0, n_pts, size=max(1, n_pts // 10))
+    q_counts[hit] = ref_counts[rng.integers(0, n_refs, size=len(hit))]   # queries sitting exactly on references
+    if n_pts > 3:
+        q_counts[1, :] = 0                                              # an empty contig
+    cen_p, cen_n = sample(n_cp, depth * 10), sample(n_cn, depth * 10)
+    cen_p[cen_p.sum(axis=1) == 0, 0] = 1
+    cen_n[cen_n.sum(axis=1) == 0, 0] = 1
+    tag = str((alpha, depth, n_pts, n_refs, n_pos, n_cp, n_cn, kn))
+    return ref_counts, n_pos, q_counts, cen_p, cen_n, kn, tag
+
+
+@pytest.mark.parametrize("round_", range(max(1, ROUNDS // 2)))
+def test_random_rounds_scoring_paths_agree(round_):
+    """Tensor-core path (first pass, list pass, decisions) against the exhaustive float64 kernel on random shapes and random
+    composition families: sparse to flat rows, shallow to very deep counts, queries that ARE references, duplicated references
+    with opposite labels (ties settled by the lower reference index on every path), near-uniform rows, empty contigs."""
+    from phamers_b200 import kmer, ops
+    rng = np.random.default_rng(99000 + round_)
+    ref_counts, n_pos, q_counts, cen_p, cen_n, kn, tag = _scoring_case(rng)
+    refs = torch.from_numpy(kmer.normalize_counts(ref_counts)).cuda()
+    cp = torch.from_numpy(kmer.normalize_counts(cen_p)).cuda()
+    cn = torch.from_numpy(kmer.normalize_counts(cen_n)).cuda()
+    counts = torch.from_numpy(q_counts.astype(np.int32)).cuda()
+    feats = ops.normalize_cuda(counts)
+    try:
+        ops.set_score_path("tc")
+        t_c = [t.cpu().numpy() for t in ops.score_cuda(counts, refs, n_pos, cp, cn, kn)]
+        t_f = [t.cpu().numpy() for t in ops.score_cuda(feats, refs, n_pos, cp, cn, kn)]
+        ops.set_score_path("exact")
+        e = [t.cpu().numpy() for t in ops.score_cuda(feats, refs, n_pos, cp, cn, kn)]
+    finally:
+        ops.set_score_path("auto")
+    tag = str(round_) + " " + tag
+    # Shallow counts give EXACT rational ties between different references; which of them a float64 sum calls nearer depends on
+    # the order of the additions (direct differences in the decision kernels, the norm expansion in the exhaustive kernel -- and a
+    # third order in scikit-learn), so the vote of such a row is not defined.  Identical reference ROWS tie bit for bit on every
+    # path and stay in the comparison: the lower index wins everywhere.
+    X, R = feats.cpu().numpy(), refs.cpu().numpy()
+    live = ~np.isnan(X[:, 0])
+    d2 = (X[live] ** 2).sum(axis=1)[:, None] + (R ** 2).sum(axis=1)[None, :] - 2.0 * X[live] @ R.T
+    order = np.argsort(d2, axis=1, kind="stable")
+    decided = np.ones(len(X), dtype=bool)
+    if R.shape[0] > kn:
+        rows = np.arange(order.shape[0])
+        a, b = order[:, kn - 1], order[:, kn]
+        close = np.abs(d2[rows, b] - d2[rows, a]) <= 1e-10 * (np.abs(d2[rows, a]) + 1e-30)
+        same_row = (R[a] == R[b]).all(axis=1)
+        decided[np.flatnonzero(live)[close & ~same_row]] = False
+    for got in (t_c, t_f):
+        assert np.array_equal(got[0][decided], e[0][decided], equal_nan=True), tag        # votes
+        ok = ~np.isnan(e[2])
+        assert np.array_equal(np.isnan(got[2]), np.isnan(e[2])), tag
+        assert np.max(np.abs(got[1][ok] - e[1][ok]), initial=0.0) <= 1e-12, tag
+        assert np.max(np.abs(got[2][ok & decided] - e[2][ok & decided]), initial=0.0) <= 1e-12, tag
