@@ -48,6 +48,7 @@ class ContigScorer(object):
 
     # -- host buffers -----------------------------------------------------------------------------------
     HOST_CHUNKS = 8                    # upload / compute pipeline depth of score_host
+    HOST_CHUNK_MIN_BASES = 1 << 22     # ... and the least bases worth a range of its own
 
     def score_host(self, seq, offsets, method="combo"):
         """seq: uint8 host tensor / ndarray with all contigs end to end (pinned memory makes the copies asynchronous), offsets:
@@ -61,7 +62,7 @@ class ContigScorer(object):
             return np.zeros((0,), dtype=np.float64)
         host_off = off_t.numpy()
         total = int(host_off[-1] - host_off[0])
-        n_chunks = max(1, min(self.HOST_CHUNKS, n, total // (1 << 22) + 1))
+        n_chunks = max(1, min(self.HOST_CHUNKS, n, total // self.HOST_CHUNK_MIN_BASES + 1))
         targets = host_off[0] + (total * np.arange(1, n_chunks, dtype=np.float64) / n_chunks)
         cuts = np.unique(np.concatenate(([0], np.clip(np.searchsorted(host_off, targets, side="left"), 0, n), [n])))
         padded = (total + 15) // 16 * 16 + 32 * len(cuts)

@@ -188,3 +188,23 @@ def test_random_rounds_scoring_paths_agree(round_):
         assert np.array_equal(np.isnan(got[2]), np.isnan(e[2])), tag
         assert np.max(np.abs(got[1][ok] - e[1][ok]), initial=0.0) <= 1e-12, tag
         assert np.max(np.abs(got[2][ok & decided] - e[2][ok & decided]), initial=0.0) <= 1e-12, tag
+
+
+@pytest.mark.parametrize("round_", range(max(1, ROUNDS // 2)))
+def test_random_rounds_host_pipeline(round_):
+    """ContigScorer.score_host (ranges of contigs uploaded on a copy stream while the previous range is counted and scored) against the
+    device-resident call on the same random workloads, with ranges small enough that every call is cut: long records that fill
+    several ranges' worth of bases on their own, empty records at the cuts, unaligned range starts."""
+    from phamers_b200 import pipeline
+    rng = np.random.default_rng(66000 + round_)
+    seq, off = _workload(rng)
+    scorer = pipeline.ContigScorer()
+    scorer.HOST_CHUNKS = int(rng.integers(2, 9))
+    scorer.HOST_CHUNK_MIN_BASES = int(rng.choice([1000, 30000, 200000]))
+    d_seq, d_off = _device(seq, off)
+    for method in ("combo", "knn", "kmeans")[: 1 + round_ % 3]:
+        _, want = scorer.score_device(d_seq, d_off, method=method, return_counts=False)
+        got = scorer.score_host(seq, off, method=method)
+        assert np.array_equal(got, want.cpu().numpy(), equal_nan=True), (round_, method)
+        pinned = torch.from_numpy(seq.copy()).pin_memory()
+        assert np.array_equal(scorer.score_host(pinned, torch.from_numpy(off.copy()), method=method), got, equal_nan=True)
